@@ -149,8 +149,8 @@ def test_planted_codes_4_and_5(orc):
         recs = orc.launch(g2, T, B, p, gpu, htsz, P0)
         assert (5, 0) in recs
         assert st.check_hit(cpu, 5, 0, wkey, P0) == secret
-    # code 4: P_0 == -+Q_k  =>  k' = 1 + p*w -+ (k+1)*2w ; X(2P) must also be in the table to be reported,
-    # so scan k for a case where the kernel reports it and check the decoding when it does
+    # code 4: P_0 == -+Q_k  =>  k' = 1 + p*w -+ (k+1)*2w.  The kernel reports it only if X(2P) probes
+    # true, so plant X(2P) as an extra table entry (w+1 items) to exercise the record and its decoding.
     hits4 = 0
     for k in range(N):
         for sign in (1, -1):
@@ -164,10 +164,12 @@ def test_planted_codes_4_and_5(orc):
             assert P0[0] == qk[0]
             recs = orc.launch(g2, T, B, p, gpu, htsz, P0)
             dbl = pyec.add(P0, P0)
-            expect4 = orc.probe_htgpu(gpu, htsz, dbl[0] & (2**64 - 1))
-            assert ((4, k) in recs) == expect4
+            assert ((4, k) in recs) == orc.probe_htgpu(gpu, htsz, dbl[0] & (2**64 - 1))
             assert not any(c in (1, 2) and i == k for c, i in recs)      # no +- probes on the equal path
-            if expect4:
-                hits4 += 1
-                assert st.check_hit(cpu, 4, k, wkey, P0) == secret
+            keys2 = np.concatenate([keys, np.array([dbl[0] & (2**64 - 1)], dtype=np.uint64)])
+            cpu2, gpu2 = orc.build_ht(keys2, htsz)
+            recs = orc.launch(g2, T, B, p, gpu2, htsz, P0)
+            assert (4, k) in recs
+            hits4 += 1
+            assert st.check_hit(cpu2, 4, k, wkey, P0) == secret
     assert hits4 > 0
