@@ -1,0 +1,386 @@
+// bsgs_b200.cu -- C ABI of libbsgs_b200.so (see include/bsgs_b200.h for the contract and the
+// reference interfaces each entry point replaces).
+#include "../../include/bsgs_b200.h"
+#include "giant_step.cuh"
+#include "host_ec.h"
+#include <cuda_runtime.h>
+#include <new>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+struct bsgs_ctx {
+    int dev = 0, last_cuda = 0, sm_count = 0;
+    uint32_t T = 0, B = 0, p = 0, htsz = 0;
+    uint64_t w = 0, N = 0, H = 0;
+    // geometry
+    uint32_t blocks_per_sm = 2, grid = 0, NT = 0, PP = 0, max_windows = 4, bucket_words = 8;
+    // device memory
+    void* d_g2_stage = nullptr;      // raw G2 image (freed after commit)
+    uint4 *d_gx = nullptr, *d_gy = nullptr, *d_chain = nullptr;
+    void* d_ht = nullptr;            // raw htGPU image: off[H+1] | tags[w]  (kept: CSR fallback)
+    uint32_t* d_buckets = nullptr;
+    uint32_t* d_hits = nullptr;      // [0] counter, [4..] records (3 u32 each)
+    unsigned long long* d_scratch = nullptr;
+    uint32_t hit_cap = 1u << 16;
+    uint32_t* h_hits = nullptr;      // pinned mirror
+    size_t chain_bytes = 0, giants_bytes = 0, table_bytes = 0;
+    bool giants_ready = false, ht_ready = false;
+    unsigned long long overfull = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+#define CU(call)                                                         \
+    do {                                                                 \
+        cudaError_t _e = (call);                                         \
+        if (_e != cudaSuccess) {                                         \
+            ctx->last_cuda = (int)_e;                                    \
+            cudaGetLastError();                                          \
+            return _e == cudaErrorMemoryAllocation ? BSGS_E_NOMEM : BSGS_E_CUDA; \
+        }                                                                \
+    } while (0)
+
+static size_t ht_image_bytes(const bsgs_ctx* c) { return (size_t)c->H * 4 + 4 + (size_t)c->w * 4; }
+
+extern "C" const char* bsgs_strerror(int s) {
+    switch (s) {
+        case BSGS_OK: return "ok";
+        case BSGS_E_ARG: return "bad argument or size mismatch";
+        case BSGS_E_CUDA: return "CUDA runtime error";
+        case BSGS_E_NOMEM: return "out of memory";
+        case BSGS_E_STATE: return "tables not uploaded";
+        case BSGS_E_LIMIT: return "parameter outside structural limits";
+        case BSGS_E_OVERFLOW: return "hit buffer overflow";
+        default: return "unknown status";
+    }
+}
+extern "C" int bsgs_last_cuda_error(const bsgs_ctx* ctx) { return ctx ? ctx->last_cuda : 0; }
+
+static void compute_geometry(bsgs_ctx* c) {
+    c->grid = (uint32_t)c->sm_count * c->blocks_per_sm;
+    c->NT = c->grid * gs::kBlock;
+    // never launch more threads than giants: shrink the grid for tiny problems (tests)
+    while (c->grid > 1 && (uint64_t)(c->grid - 1) * gs::kBlock >= c->N) c->grid--;
+    c->NT = c->grid * gs::kBlock;
+    c->PP = (uint32_t)((c->N + c->NT - 1) / c->NT);
+}
+
+extern "C" int bsgs_create(bsgs_ctx** out, int device, uint32_t T, uint32_t B, uint32_t p, uint64_t w, uint32_t htsz) {
+    if (!out) return BSGS_E_ARG;
+    *out = nullptr;
+    if (!T || !B || !p || !w) return BSGS_E_ARG;
+    uint64_t N = (uint64_t)T * B * p;
+    if (N >= (1ull << 31) || htsz > 31 || htsz < 1 || w >= (1ull << 32)) return BSGS_E_LIMIT;   // u32 indices/tags (F197:2584, 4412-4416)
+    bsgs_ctx* ctx = new (std::nothrow) bsgs_ctx();
+    if (!ctx) return BSGS_E_NOMEM;
+    ctx->dev = device; ctx->T = T; ctx->B = B; ctx->p = p; ctx->w = w; ctx->htsz = htsz; ctx->N = N; ctx->H = 1ull << htsz;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->e1);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_hits, 16 + (size_t)ctx->hit_cap * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_scratch, 64);
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_hits, 16 + (size_t)ctx->hit_cap * 12);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_hits, 0, 16, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { int rc = e == cudaErrorMemoryAllocation ? BSGS_E_NOMEM : BSGS_E_CUDA; bsgs_destroy(ctx); cudaGetLastError(); return rc; }
+    compute_geometry(ctx);
+    *out = ctx;
+    return BSGS_OK;
+}
+
+extern "C" void bsgs_destroy(bsgs_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->dev);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_g2_stage); cudaFree(ctx->d_gx); cudaFree(ctx->d_gy); cudaFree(ctx->d_chain);
+    cudaFree(ctx->d_ht); cudaFree(ctx->d_buckets); cudaFree(ctx->d_hits); cudaFree(ctx->d_scratch);
+    if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
+    if (ctx->e0) cudaEventDestroy(ctx->e0);
+    if (ctx->e1) cudaEventDestroy(ctx->e1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
+    delete ctx;
+}
+
+extern "C" int bsgs_set_option(bsgs_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return BSGS_E_ARG;
+    if (ctx->d_gx || ctx->d_buckets) return BSGS_E_STATE;       // geometry is baked into the layouts
+    if (!strcmp(name, "blocks_per_sm")) { if (value < 1 || value > 8) return BSGS_E_ARG; ctx->blocks_per_sm = (uint32_t)value; compute_geometry(ctx); return BSGS_OK; }
+    if (!strcmp(name, "bucket_bytes")) { if (value != 32 && value != 64) return BSGS_E_ARG; ctx->bucket_words = (uint32_t)(value / 4); return BSGS_OK; }
+    if (!strcmp(name, "max_windows")) { if (value < 1 || value > BSGS_MAX_WINDOWS) return BSGS_E_ARG; ctx->max_windows = (uint32_t)value; return BSGS_OK; }
+    return BSGS_E_ARG;
+}
+
+extern "C" int bsgs_get_info(const bsgs_ctx* ctx, bsgs_info* info) {
+    if (!ctx || !info) return BSGS_E_ARG;
+    info->grid = ctx->grid; info->block = gs::kBlock; info->points_per_thread = ctx->PP; info->sm_count = (uint32_t)ctx->sm_count;
+    info->n_giants = ctx->N; info->bytes_giants = ctx->giants_bytes; info->bytes_chain = ctx->chain_bytes; info->bytes_table = ctx->table_bytes;
+    return BSGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ tables
+extern "C" int bsgs_giants_staging(bsgs_ctx* ctx, void** dev_ptr, size_t* bytes) {
+    if (!ctx || !dev_ptr || !bytes) return BSGS_E_ARG;
+    CU(cudaSetDevice(ctx->dev));
+    if (!ctx->d_g2_stage) CU(cudaMalloc(&ctx->d_g2_stage, (size_t)ctx->N * 64));
+    *dev_ptr = ctx->d_g2_stage; *bytes = (size_t)ctx->N * 64;
+    return BSGS_OK;
+}
+extern "C" int bsgs_giants_commit(bsgs_ctx* ctx) {
+    if (!ctx || !ctx->d_g2_stage) return BSGS_E_STATE;
+    CU(cudaSetDevice(ctx->dev));
+    size_t slots = (size_t)ctx->NT * ctx->PP;
+    if (!ctx->d_gx) {
+        CU(cudaMalloc(&ctx->d_gx, slots * 32));
+        CU(cudaMalloc(&ctx->d_gy, slots * 32));
+        ctx->chain_bytes = slots * 32 * ctx->max_windows;
+        CU(cudaMalloc(&ctx->d_chain, ctx->chain_bytes));
+        ctx->giants_bytes = slots * 64;
+    }
+    uint32_t blocks = (uint32_t)((slots + 255) / 256);
+    gs::k_convert_g2<<<blocks, 256, 0, ctx->stream>>>((const uint32_t*)ctx->d_g2_stage, ctx->d_gx, ctx->d_gy, ctx->T, ctx->B, ctx->p,
+                                                     (uint32_t)ctx->N, ctx->NT, ctx->PP);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(ctx->d_g2_stage)); ctx->d_g2_stage = nullptr;
+    ctx->giants_ready = true;
+    return BSGS_OK;
+}
+extern "C" int bsgs_upload_giants(bsgs_ctx* ctx, const void* g2, size_t bytes) {
+    if (!ctx || !g2 || bytes != (size_t)ctx->N * 64) return BSGS_E_ARG;
+    void* d; size_t n; int rc = bsgs_giants_staging(ctx, &d, &n);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(d, g2, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return bsgs_giants_commit(ctx);
+}
+
+extern "C" int bsgs_ht_staging(bsgs_ctx* ctx, void** dev_ptr, size_t* bytes) {
+    if (!ctx || !dev_ptr || !bytes) return BSGS_E_ARG;
+    CU(cudaSetDevice(ctx->dev));
+    if (!ctx->d_ht) CU(cudaMalloc(&ctx->d_ht, ht_image_bytes(ctx) + 64));
+    *dev_ptr = ctx->d_ht; *bytes = ht_image_bytes(ctx);
+    return BSGS_OK;
+}
+extern "C" int bsgs_ht_commit(bsgs_ctx* ctx) {
+    if (!ctx || !ctx->d_ht) return BSGS_E_STATE;
+    CU(cudaSetDevice(ctx->dev));
+    size_t bbytes = (size_t)ctx->H * ctx->bucket_words * 4;
+    if (!ctx->d_buckets) CU(cudaMalloc(&ctx->d_buckets, bbytes));
+    ctx->table_bytes = bbytes + ht_image_bytes(ctx);
+    const uint32_t* off = (const uint32_t*)ctx->d_ht;
+    const uint32_t* tags = off + ctx->H + 1;
+    CU(cudaMemsetAsync(ctx->d_scratch, 0, 8, ctx->stream));
+    uint32_t blocks = (uint32_t)((ctx->H + 255) / 256);
+    if (ctx->bucket_words == 8) gs::k_build_buckets<8><<<blocks, 256, 0, ctx->stream>>>(off, tags, ctx->d_buckets, ctx->H, ctx->d_scratch);
+    else gs::k_build_buckets<16><<<blocks, 256, 0, ctx->stream>>>(off, tags, ctx->d_buckets, ctx->H, ctx->d_scratch);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&ctx->overfull, ctx->d_scratch, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->ht_ready = true;
+    return BSGS_OK;
+}
+extern "C" int bsgs_upload_ht(bsgs_ctx* ctx, const void* htgpu, size_t bytes) {
+    if (!ctx || !htgpu || bytes != ht_image_bytes(ctx)) return BSGS_E_ARG;
+    void* d; size_t n; int rc = bsgs_ht_staging(ctx, &d, &n);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(d, htgpu, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return bsgs_ht_commit(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------ hot path
+static gs::Tables make_tables(const bsgs_ctx* c) {
+    gs::Tables tb;
+    tb.gx = c->d_gx; tb.gy = c->d_gy; tb.chain = c->d_chain; tb.buckets = c->d_buckets;
+    tb.csr_off = (const uint32_t*)c->d_ht; tb.csr_tags = tb.csr_off + c->H + 1;
+    tb.hit_count = c->d_hits; tb.hits = c->d_hits + 4; tb.hit_cap = c->hit_cap;
+    tb.NT = c->NT; tb.PP = c->PP; tb.N = (uint32_t)c->N; tb.mask = (uint32_t)(c->H - 1);
+    return tb;
+}
+
+static void fill_win(gs::WinConst& wc, const uint8_t* pxy) {
+    hec::Fe x, y, nx, y2;
+    hec::load_le(x, pxy); hec::load_le(y, pxy + 32);
+    hec::neg(nx, x); hec::add(y2, y, y);
+    memcpy(wc.px, x.v, 32); memcpy(wc.py, y.v, 32); memcpy(wc.npx, nx.v, 32); memcpy(wc.py2, y2.v, 32);
+}
+
+template <int W>
+static cudaError_t launch_w(const bsgs_ctx* c, const uint8_t* pxy) {
+    gs::StepParams<W> sp;
+    for (int i = 0; i < W; i++) fill_win(sp.win[i], pxy + 64 * i);
+    gs::Tables tb = make_tables(c);
+    if (c->bucket_words == 8) gs::k_giant_step<W, 8><<<c->grid, gs::kBlock, 0, c->stream>>>(tb, sp);
+    else gs::k_giant_step<W, 16><<<c->grid, gs::kBlock, 0, c->stream>>>(tb, sp);
+    return cudaGetLastError();
+}
+static cudaError_t launch_any(const bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
+    switch (nwin) {
+        case 1: return launch_w<1>(c, pxy);
+        case 2: return launch_w<2>(c, pxy);
+        case 3: return launch_w<3>(c, pxy);
+        case 4: return launch_w<4>(c, pxy);
+        case 5: return launch_w<5>(c, pxy);
+        case 6: return launch_w<6>(c, pxy);
+        case 7: return launch_w<7>(c, pxy);
+        case 8: return launch_w<8>(c, pxy);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// read back counter + records, clear the counter; appends to out[*nhits...] with window offset
+static int collect_hits(bsgs_ctx* ctx, uint32_t window_base, bsgs_hit* out, uint32_t cap, uint32_t* nhits) {
+    const uint32_t eager = 64;                                   // one D2H covers the common case
+    CU(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, 16 + eager * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    uint32_t cnt = ctx->h_hits[0];
+    if (cnt == 0) return BSGS_OK;
+    uint32_t stored = cnt < ctx->hit_cap ? cnt : ctx->hit_cap;
+    if (stored > eager) {
+        CU(cudaMemcpyAsync(ctx->h_hits + 4 + eager * 3, ctx->d_hits + 4 + eager * 3, (size_t)(stored - eager) * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaMemsetAsync(ctx->d_hits, 0, 4, ctx->stream));         // F197:2500-2504
+    CU(cudaStreamSynchronize(ctx->stream));
+    int rc = cnt > ctx->hit_cap ? BSGS_E_OVERFLOW : BSGS_OK;
+    for (uint32_t i = 0; i < stored; i++) {
+        uint32_t pos = *nhits;
+        if (pos < cap && out) {
+            out[pos].code = ctx->h_hits[4 + 3 * i]; out[pos].idx = ctx->h_hits[4 + 3 * i + 1];
+            out[pos].window = window_base + ctx->h_hits[4 + 3 * i + 2]; out[pos].reserved = 0;
+        } else rc = BSGS_E_OVERFLOW;
+        (*nhits)++;
+    }
+    return rc;
+}
+
+extern "C" int bsgs_step_multi(bsgs_ctx* ctx, uint32_t nwin, const uint8_t* pxy_le, bsgs_hit* out, uint32_t cap, uint32_t* nhits) {
+    if (!ctx || !pxy_le || !nhits || nwin < 1 || nwin > ctx->max_windows) return BSGS_E_ARG;
+    if (!ctx->giants_ready || !ctx->ht_ready) return BSGS_E_STATE;
+    *nhits = 0;
+    CU(cudaSetDevice(ctx->dev));
+    CU(launch_any(ctx, nwin, pxy_le));
+    return collect_hits(ctx, 0, out, cap, nhits);
+}
+extern "C" int bsgs_step(bsgs_ctx* ctx, const uint8_t px_le[32], const uint8_t py_le[32], bsgs_hit* out, uint32_t cap, uint32_t* nhits) {
+    if (!px_le || !py_le) return BSGS_E_ARG;
+    uint8_t pxy[64]; memcpy(pxy, px_le, 32); memcpy(pxy + 32, py_le, 32);
+    return bsgs_step_multi(ctx, 1, pxy, out, cap, nhits);
+}
+
+extern "C" int bsgs_run(bsgs_ctx* ctx, const uint8_t p0xy_le[64], const uint8_t dxy_le[64], uint64_t nwindows, uint32_t batch,
+                        uint32_t stop_after_hits, bsgs_hit* out, uint32_t cap, uint32_t* nhits, uint64_t* windows_done) {
+    if (!ctx || !p0xy_le || !dxy_le || !nhits) return BSGS_E_ARG;
+    if (!ctx->giants_ready || !ctx->ht_ready) return BSGS_E_STATE;
+    if (batch < 1 || batch > ctx->max_windows) return BSGS_E_ARG;
+    *nhits = 0;
+    CU(cudaSetDevice(ctx->dev));
+    hec::Pt P, D;
+    hec::load_le(P.x, p0xy_le); hec::load_le(P.y, p0xy_le + 32);
+    hec::load_le(D.x, dxy_le); hec::load_le(D.y, dxy_le + 32);
+    uint64_t done = 0; int rc = BSGS_OK;
+    uint8_t cur[BSGS_MAX_WINDOWS * 64], nxt[BSGS_MAX_WINDOWS * 64];
+    auto fill = [&](uint8_t* buf, uint32_t n) {                 // GetJob (F197:2077-2092), n windows ahead
+        for (uint32_t i = 0; i < n; i++) { hec::store_le(buf + 64 * i, P.x); hec::store_le(buf + 64 * i + 32, P.y); hec::pt_add(P, P, D); }
+    };
+    uint32_t n = (uint32_t)(nwindows - done < batch ? nwindows - done : batch);
+    if (n) fill(cur, n);
+    while (done < nwindows) {
+        CU(launch_any(ctx, n, cur));
+        // overlap: derive the next batch of base points on the host while the kernel runs
+        uint64_t left = nwindows - done - n;
+        uint32_t n2 = (uint32_t)(left < batch ? left : batch);
+        if (n2) fill(nxt, n2);
+        int r2 = collect_hits(ctx, (uint32_t)done, out, cap, nhits);
+        done += n;
+        if (r2 && r2 != BSGS_E_OVERFLOW) { rc = r2; break; }
+        if (r2 == BSGS_E_OVERFLOW) rc = r2;
+        if (stop_after_hits && *nhits >= stop_after_hits) break;
+        memcpy(cur, nxt, sizeof cur); n = n2;
+    }
+    if (windows_done) *windows_done = done;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ measurement
+extern "C" int bsgs_time_launches(bsgs_ctx* ctx, uint32_t nwin, const uint8_t* pxy_le, uint32_t iters, float* ms) {
+    if (!ctx || !pxy_le || !ms || nwin < 1 || nwin > ctx->max_windows || !iters) return BSGS_E_ARG;
+    if (!ctx->giants_ready || !ctx->ht_ready) return BSGS_E_STATE;
+    CU(cudaSetDevice(ctx->dev));
+    CU(cudaEventRecord(ctx->e0, ctx->stream));
+    for (uint32_t i = 0; i < iters; i++) CU(launch_any(ctx, nwin, pxy_le));
+    CU(cudaEventRecord(ctx->e1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->e1));
+    CU(cudaEventElapsedTime(ms, ctx->e0, ctx->e1));
+    CU(cudaMemsetAsync(ctx->d_hits, 0, 4, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BSGS_OK;
+}
+
+extern "C" int bsgs_probe_bench(bsgs_ctx* ctx, uint64_t nkeys, uint64_t seed, uint32_t iters, float* ms, uint64_t* nfound) {
+    if (!ctx || !ms || !iters) return BSGS_E_ARG;
+    if (!ctx->ht_ready) return BSGS_E_STATE;
+    CU(cudaSetDevice(ctx->dev));
+    gs::Tables tb = make_tables(ctx);
+    CU(cudaMemsetAsync(ctx->d_scratch, 0, 8, ctx->stream));
+    uint32_t grid = (uint32_t)ctx->sm_count * 8;
+    CU(cudaEventRecord(ctx->e0, ctx->stream));
+    for (uint32_t i = 0; i < iters; i++) {
+        if (ctx->bucket_words == 8) gs::k_probe_bench<8><<<grid, 256, 0, ctx->stream>>>(tb, nkeys, seed + i * nkeys, ctx->d_scratch);
+        else gs::k_probe_bench<16><<<grid, 256, 0, ctx->stream>>>(tb, nkeys, seed + i * nkeys, ctx->d_scratch);
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->e1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->e1));
+    CU(cudaEventElapsedTime(ms, ctx->e0, ctx->e1));
+    unsigned long long f = 0;
+    CU(cudaMemcpyAsync(&f, ctx->d_scratch, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (nfound) *nfound = f;
+    return BSGS_OK;
+}
+
+extern "C" int bsgs_probe_keys(bsgs_ctx* ctx, const uint64_t* keys, uint64_t nkeys, uint8_t* found) {
+    if (!ctx || !keys || !found) return BSGS_E_ARG;
+    if (!ctx->ht_ready) return BSGS_E_STATE;
+    if (!nkeys) return BSGS_OK;
+    CU(cudaSetDevice(ctx->dev));
+    uint64_t* dk = nullptr; uint8_t* df = nullptr;
+    CU(cudaMalloc(&dk, nkeys * 8));
+    cudaError_t e = cudaMalloc(&df, nkeys);
+    if (e != cudaSuccess) { cudaFree(dk); ctx->last_cuda = e; cudaGetLastError(); return BSGS_E_NOMEM; }
+    gs::Tables tb = make_tables(ctx);
+    e = cudaMemcpyAsync(dk, keys, nkeys * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        uint32_t blocks = (uint32_t)((nkeys + 255) / 256);
+        if (ctx->bucket_words == 8) gs::k_probe_keys<8><<<blocks, 256, 0, ctx->stream>>>(tb, dk, nkeys, df);
+        else gs::k_probe_keys<16><<<blocks, 256, 0, ctx->stream>>>(tb, dk, nkeys, df);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(found, df, nkeys, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dk); cudaFree(df);
+    if (e != cudaSuccess) { ctx->last_cuda = e; cudaGetLastError(); return BSGS_E_CUDA; }
+    return BSGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ diagnostics
+extern "C" int bsgs_debug_field(int device, int op, const uint32_t* a, const uint32_t* b, uint32_t* r, uint32_t n) {
+    if (!a || !b || !r || !n) return BSGS_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return BSGS_E_CUDA;
+    uint32_t *da = nullptr, *db = nullptr, *dr = nullptr; size_t bytes = (size_t)n * 32;
+    cudaError_t e = cudaMalloc(&da, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&db, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&dr, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { gs::k_debug_field<<<(n + 127) / 128, 128>>>(op, da, db, dr, n); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpy(r, dr, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(db); cudaFree(dr);
+    if (e != cudaSuccess) { cudaGetLastError(); return BSGS_E_CUDA; }
+    return BSGS_OK;
+}

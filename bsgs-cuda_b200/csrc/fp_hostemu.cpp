@@ -1,0 +1,12 @@
+// fp_hostemu.cpp -- exports fp.cuh compiled for the HOST (PTX primitives emulated) so that the limb
+// arithmetic can be unit-tested on a machine without a GPU.  Test-only; not linked into the product.
+#include "fp.cuh"
+extern "C" {
+void he_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) { fp::fe_mul(r, a, b); }
+void he_sqr(uint32_t* r, const uint32_t* a) { fp::fe_sqr(r, a); }
+void he_inv(uint32_t* r, const uint32_t* a) { fp::fe_inv(r, a); }
+void he_sub_canon(uint32_t* r, const uint32_t* a, const uint32_t* b) { fp::fe_sub_canon(r, a, b); }
+void he_add_lazy(uint32_t* r, const uint32_t* a, const uint32_t* b) { fp::fe_add_lazy(r, a, b); }
+void he_canon(uint32_t* r) { fp::fe_canon(r); }
+uint64_t he_add_low64_canon(const uint32_t* a, const uint32_t* u) { return fp::fe_add_low64_canon(a, u); }
+}

@@ -1,0 +1,117 @@
+/*
+ * bsgs_b200.h -- C ABI of libbsgs_b200.so, the B200-native drop-in for the GPU giant-step path of
+ * Etayson/BSGS-cuda.
+ *
+ * What this boundary replaces in the reference (1_9_7File.pb, "F197"):
+ *   - the CUDA *driver API* import table and the embedded PTX module  F197:55-106, 5181-23979
+ *   - the per-GPU worker's device set-up                              F197:2181-2353  (cuda())
+ *   - the per-launch sequence: 64 B H2D of the base point, launch of `_test1`, sync, read-back of
+ *     the hit counter and of the {code, idx} records                   F197:2435-2509
+ * The reference host keeps: CLI parsing, table files, GetJob (F197:2077-2092), checkerThread
+ * (F197:3933-4296).  A PureBasic host binds these symbols with `ImportC "libbsgs_b200.so"` instead of
+ * `Import "lib\cuda.lib"` -- see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all big integers are 32-byte LITTLE-ENDIAN, exactly the
+ *     in-memory form of the reference host (lib/Curve64.pb:450-473, m_sethex32), i.e. the bytes the
+ *     reference hands to swap32() before its H2D copy (F197:2435-2439);
+ *   - every function returns 0 on success or a negative bsgs_status; nothing aborts, prompts or
+ *     prints (the reference's exit() blocks on Input(), F197:754-764);
+ *   - a context is bound to one device and must be driven by one thread at a time; distinct
+ *     contexts may be driven concurrently from distinct threads (one per GPU, like F197:4776);
+ *   - the library copies on upload: the caller may free host buffers immediately
+ *     (the reference frees them from main after all GPU threads copied, F197:4822-4843).
+ */
+#ifndef BSGS_B200_H
+#define BSGS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bsgs_ctx bsgs_ctx;
+
+/* One hit record.  `code` and `idx` have the reference's meaning (F197:2475-2490):
+ *   1: X(P + Q_idx) probes true      2: X(P - Q_idx) probes true
+ *   4: P.x == Q_idx.x and X(2P) probes true      5: P.x itself probes true (idx = 0)
+ * `window` is the index of the base point inside a multi-window call (0 for bsgs_step). */
+typedef struct { uint32_t code, idx, window, reserved; } bsgs_hit;
+
+typedef enum {
+    BSGS_OK = 0,
+    BSGS_E_ARG = -1,          /* bad argument / size mismatch */
+    BSGS_E_CUDA = -2,         /* CUDA runtime error, see bsgs_last_cuda_error() */
+    BSGS_E_NOMEM = -3,        /* device or host allocation failed */
+    BSGS_E_STATE = -4,        /* tables not uploaded / committed yet */
+    BSGS_E_LIMIT = -5,        /* parameter outside structural limits (N >= 2^32, htsz > 31, w >= 2^32) */
+    BSGS_E_OVERFLOW = -6      /* more hits than `cap`; *nhits holds the true count, `cap` were stored */
+} bsgs_status;
+
+/* -- lifetime ------------------------------------------------------------------------------ */
+/* T,B,p,w,htsz are the reference's -t -b -p -w -htsz (w already parsed to an item count).
+ * Replaces cuInit/cuCtxCreate/cuModuleLoadData/cuMemAlloc (F197:2181-2255). */
+int  bsgs_create(bsgs_ctx **out, int device, uint32_t T, uint32_t B, uint32_t p, uint64_t w, uint32_t htsz);
+void bsgs_destroy(bsgs_ctx *ctx);
+const char *bsgs_strerror(int status);
+int  bsgs_last_cuda_error(const bsgs_ctx *ctx);            /* cudaError_t of the last failure */
+
+/* -- tables -------------------------------------------------------------------------------- */
+/* `g2` = the bytes of <T>_<B>_<p>_<w>_g2.BIN as they are (N*64 bytes; F197:1905-2058).
+ * Replaces cuMemcpyHtoD of *GiantArrPacked (F197:2337). */
+int  bsgs_upload_giants(bsgs_ctx *ctx, const void *g2, size_t bytes);
+/* `htgpu` = the bytes of <Gx>_<w>_<H>_htGPUv0.BIN as they are (4H + 4 + 4w bytes; F197:3337-3444).
+ * Replaces cuMemcpyHtoD of *GpuHT (F197:2350). */
+int  bsgs_upload_ht(bsgs_ctx *ctx, const void *htgpu, size_t bytes);
+/* Two-phase variants for multi-GPU start-up: obtain the device staging buffer (so that an NCCL
+ * broadcast can land the image in place), then commit (build the in-HBM layouts). */
+int  bsgs_giants_staging(bsgs_ctx *ctx, void **dev_ptr, size_t *bytes);
+int  bsgs_giants_commit(bsgs_ctx *ctx);
+int  bsgs_ht_staging(bsgs_ctx *ctx, void **dev_ptr, size_t *bytes);
+int  bsgs_ht_commit(bsgs_ctx *ctx);
+
+/* -- the hot path -------------------------------------------------------------------------- */
+/* One reference launch: same base point, same (code, idx) multiset as `_test1` (order is not part
+ * of the contract).  Replaces F197:2435-2509.  `cap` bounds the record buffer explicitly (the
+ * reference overflows into the giant array at record 240, F197:2337 / PTX197:L104-109). */
+int  bsgs_step(bsgs_ctx *ctx, const uint8_t px_le[32], const uint8_t py_le[32],
+               bsgs_hit *out, uint32_t cap, uint32_t *nhits);
+/* nwin (1..BSGS_MAX_WINDOWS) consecutive GetJob() windows in ONE launch: pxy_le holds nwin records
+ * of 64 bytes (x then y).  Each giant point is loaded once for all windows and one field inversion
+ * per thread is shared by all of them.  hits carry the window index. */
+#define BSGS_MAX_WINDOWS 8
+int  bsgs_step_multi(bsgs_ctx *ctx, uint32_t nwin, const uint8_t *pxy_le,
+                     bsgs_hit *out, uint32_t cap, uint32_t *nhits);
+/* Whole search loop on the library side: windows j = 0..nwindows-1 with base points
+ * P_j = P0 + j*D (D = PUBADDBIG, F197:4759-4765), `batch` windows per launch, stops early after the
+ * launch in which `stop_after_hits` records have been collected (0 = never).  hit.window = j. */
+int  bsgs_run(bsgs_ctx *ctx, const uint8_t p0xy_le[64], const uint8_t dxy_le[64], uint64_t nwindows,
+              uint32_t batch, uint32_t stop_after_hits, bsgs_hit *out, uint32_t cap, uint32_t *nhits,
+              uint64_t *windows_done);
+
+/* -- measurement helpers (used by bench.py; device-resident timing with CUDA events) -------- */
+/* `iters` back-to-back launches of nwin windows each on the context's stream; returns the elapsed
+ * device time of the whole train in *ms (CUDA events on the launching stream). */
+int  bsgs_time_launches(bsgs_ctx *ctx, uint32_t nwin, const uint8_t *pxy_le, uint32_t iters, float *ms);
+/* probe-only micro-kernel: nkeys pseudo-random 64-bit keys (splitmix64 of seed)
+ * probed against the uploaded table; returns device ms and the number of keys that probed true. */
+int  bsgs_probe_bench(bsgs_ctx *ctx, uint64_t nkeys, uint64_t seed, uint32_t iters, float *ms, uint64_t *nfound);
+/* exact probe of caller-supplied keys (for parity tests of the table layouts) */
+int  bsgs_probe_keys(bsgs_ctx *ctx, const uint64_t *keys, uint64_t nkeys, uint8_t *found);
+/* geometry actually used by the kernel (threads, points per thread, bytes resident) */
+typedef struct { uint32_t grid, block, points_per_thread, sm_count; uint64_t n_giants, bytes_giants, bytes_chain, bytes_table; } bsgs_info;
+int  bsgs_get_info(const bsgs_ctx *ctx, bsgs_info *info);
+/* tuning knobs: "blocks_per_sm", "bucket_bytes" (32|64), "max_windows"; call before uploads */
+int  bsgs_set_option(bsgs_ctx *ctx, const char *name, int64_t value);
+
+/* -- diagnostics ---------------------------------------------------------------------------- */
+/* element-wise field operation on n pairs of 8 x u32 little-endian limbs, executed on the device
+ * (op: 0 mul, 1 sqr, 2 inv, 3 sub(canonical), 4 add(lazy), 5 canonicalise, 6 low64 of canonical
+ * (a+b), 7 low64 of X(2P) given (Px, 1/(2Py))).  Used by the parity tests of the limb arithmetic. */
+int  bsgs_debug_field(int device, int op, const uint32_t *a, const uint32_t *b, uint32_t *r, uint32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,267 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI of libbsgs_b200.so) against the CPU
+oracle, and against the reference's own kernel (oracle/_ref, when present) on identical inputs.
+Bit-exact: integer work, sorted multisets of (code, idx)."""
+import os
+import random
+import numpy as np
+import pytest
+from tests import pyec
+from tests.helpers import M64, random_point, giant, candidate_x, synthetic_keys, norm_hits
+
+pytestmark = pytest.mark.gpu
+P = pyec.P
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import bsgs_cuda_b200 as b
+    b.native.load()
+    return b
+
+
+# ------------------------------------------------------------------ limb arithmetic on the device
+def test_field_ops_on_device(pkg):
+    rnd = random.Random(7)
+    edge = [0, 1, 2, P - 1, P, P + 1, 2**256 - 1, 2**256 - 2, 2**255, 977, 2**32 + 977, 2**224 - 1,
+            (2**256 - 1) ^ (2**64 - 1), 2**256 - 2**96, 2**256 - 2**32 - 978, P - 977]
+    a = edge + [rnd.getrandbits(256) for _ in range(3000)]
+    b = [a[rnd.randrange(len(a))] for _ in a]
+    dbg = pkg.native.debug_field
+    assert [x % P for x in dbg(0, a, b)] == [x * y % P for x, y in zip(a, b)]
+    assert [x % P for x in dbg(1, a, b)] == [x * x % P for x in a]
+    ac, bc = [x % P for x in a], [x % P for x in b]
+    assert dbg(3, ac, bc) == [(x - y) % P for x, y in zip(ac, bc)]
+    r = dbg(4, ac, bc)
+    assert all(v < 2**256 for v in r) and [v % P for v in r] == [(x + y) % P for x, y in zip(ac, bc)]
+    assert dbg(5, a, b) == [x % P if x < 2 * P else None for x in a]
+    assert [v & M64 for v in dbg(6, a, bc)] == [((x + y) % P) & M64 for x, y in zip(a, bc)]
+    sub = a[:256]
+    assert [x % P for x in dbg(2, sub, sub)] == [pow(x % P, P - 2, P) for x in sub]
+    # X(2P) low 64 bits from (Px, 1/(2Py))
+    pts = [random_point(rnd) for _ in range(32)]
+    got = dbg(7, [p[0] for p in pts], [pow(2 * p[1], -1, P) for p in pts])
+    assert [g & M64 for g in got] == [pyec.add(p, p)[0] & M64 for p in pts]
+
+
+def test_low64_slow_path_on_device(pkg):
+    """Values whose upper limbs are all ones exercise the exact branch of fe_add_low64_canon."""
+    rnd = random.Random(11)
+    a, u = [], []
+    for _ in range(500):
+        hi = (2**256 - 1) ^ (2**96 - 1)
+        a.append(hi | rnd.getrandbits(96)); u.append(rnd.randrange(P))
+        a.append(rnd.getrandbits(256)); u.append(P - 1 - rnd.getrandbits(40))
+        x = rnd.getrandbits(256); a.append(x); u.append((hi | rnd.getrandbits(96)) % P if x else 0)
+        a.append(2**256 - 1 - rnd.getrandbits(34)); u.append(P - 1 - rnd.getrandbits(34))
+    got = pkg.native.debug_field(6, a, u)
+    assert [v & M64 for v in got] == [((x + y) % P) & M64 for x, y in zip(a, u)]
+
+
+# ------------------------------------------------------------------ table layouts
+@pytest.mark.parametrize("bucket_bytes", [32, 64])
+@pytest.mark.parametrize("w,htsz", [(50000, 14), (50000, 9), (3000, 12), (1, 1)])
+def test_probe_layout_vs_oracle(pkg, orc, w, htsz, bucket_bytes):
+    keys = synthetic_keys(w, [], seed=w + htsz)
+    _, gpu = orc.build_ht(keys, htsz)
+    with pkg.Engine(4, 4, 4, w, htsz, bucket_bytes=bucket_bytes) as e:
+        e.upload_ht(gpu)
+        rs = np.random.RandomState(3)
+        q = np.concatenate([keys[rs.randint(0, w, size=4000)],                        # members
+                            rs.randint(0, 2**62, size=4000).astype(np.uint64),             # random
+                            keys[rs.randint(0, w, size=4000)] ^ np.uint64(1 << 40),        # same bucket, other tag
+                            keys[rs.randint(0, w, size=2000)] ^ np.uint64(1 << 20)])       # bits the table ignores
+        got = e.probe_keys(q)
+        exp = np.array([orc.probe_htgpu(gpu, htsz, int(k)) for k in q])
+        assert np.array_equal(got, exp)
+        assert got[:4000].all()
+
+
+# ------------------------------------------------------------------ one launch
+CASES = [
+    # T, B, p, w, htsz, blocks_per_sm
+    (32, 4, 16, 4096, 10, 2),          # N = 2048: one point per thread
+    (7, 3, 5, 1000, 8, 2),             # ragged N = 105
+    (64, 20, 100, 60000, 14, 1),       # N = 128000 > one wave of threads: several points per thread
+    (128, 2, 8, 5000, 4, 2),           # load 312 per bucket: every probe takes the CSR fallback
+]
+
+
+def build_case(orc, T, B, p, w, htsz, seed, nplant=24):
+    rnd = random.Random(seed)
+    N = T * B * p
+    Ppt = random_point(rnd)
+    plant = []
+    for i in range(nplant):
+        k = rnd.randrange(N) if i > 3 else (0, N - 1, N // 2, 1 % N)[i]
+        plant.append((1 + (i & 1), k))
+    xs = [candidate_x(Ppt, w, k, c) for c, k in plant]
+    keys = synthetic_keys(w, xs, seed)
+    cpu, gpu = orc.build_ht(keys, htsz)
+    g2 = orc.build_g2(T, B, p, w)
+    return Ppt, plant, cpu, gpu, g2
+
+
+@pytest.mark.parametrize("bucket_bytes", [32, 64])
+@pytest.mark.parametrize("case", CASES)
+def test_step_matches_oracle(pkg, orc, case, bucket_bytes):
+    T, B, p, w, htsz, bps = case
+    Ppt, plant, cpu, gpu, g2 = build_case(orc, T, B, p, w, htsz, seed=T * 1000 + p)
+    exp = orc.launch(g2, T, B, p, gpu, htsz, Ppt)
+    assert set(plant) <= set(exp)                      # planted hits are real hits of the oracle
+    with pkg.Engine(T, B, p, w, htsz, bucket_bytes=bucket_bytes, blocks_per_sm=bps) as e:
+        e.upload_giants(g2); e.upload_ht(gpu)
+        assert norm_hits(e.step(Ppt)) == norm_hits(exp)
+        # same engine, other base points (tables stay resident, like the reference's launch loop)
+        rnd = random.Random(99)
+        for _ in range(2):
+            Q = random_point(rnd)
+            assert norm_hits(e.step(Q)) == norm_hits(orc.launch(g2, T, B, p, gpu, htsz, Q))
+
+
+@pytest.mark.parametrize("nwin", [2, 3, 4])
+def test_multi_window_equals_separate_launches(pkg, orc, nwin):
+    T, B, p, w, htsz = 32, 8, 12, 20000, 12
+    rnd = random.Random(nwin)
+    pts = [random_point(rnd) for _ in range(nwin)]
+    N = T * B * p
+    plant = [(i % nwin, 1 + (i & 1), rnd.randrange(N)) for i in range(16)]
+    xs = [candidate_x(pts[wi], w, k, c) for wi, c, k in plant]
+    keys = synthetic_keys(w, xs, 5)
+    cpu, gpu = orc.build_ht(keys, htsz)
+    g2 = orc.build_g2(T, B, p, w)
+    with pkg.Engine(T, B, p, w, htsz) as e:
+        e.upload_giants(g2); e.upload_ht(gpu)
+        got = sorted((win, c, 0 if c == 5 else i) for c, i, win in e.step_multi(pts))
+        exp = sorted((wi, c, 0 if c == 5 else i) for wi in range(nwin) for c, i in orc.launch(g2, T, B, p, gpu, htsz, pts[wi]))
+        assert got == exp
+        assert {(wi, c, k) for wi, c, k in plant} <= set(got)
+
+
+def test_max_windows_8(pkg, orc):
+    T, B, p, w, htsz = 16, 4, 6, 3000, 9
+    rnd = random.Random(8)
+    pts = [random_point(rnd) for _ in range(8)]
+    xs = [candidate_x(pts[i], w, (i * 37) % (T * B * p), 1 + (i & 1)) for i in range(8)]
+    cpu, gpu = orc.build_ht(synthetic_keys(w, xs, 8), htsz)
+    g2 = orc.build_g2(T, B, p, w)
+    with pkg.Engine(T, B, p, w, htsz, max_windows=8) as e:
+        e.upload_giants(g2); e.upload_ht(gpu)
+        got = sorted((win, c, 0 if c == 5 else i) for c, i, win in e.step_multi(pts))
+        exp = sorted((wi, c, 0 if c == 5 else i) for wi in range(8) for c, i in orc.launch(g2, T, B, p, gpu, htsz, pts[wi]))
+        assert got == exp and len(got) >= 8
+
+
+def test_planted_codes_4_and_5(pkg, orc):
+    T, B, p, w, htsz = 16, 4, 8, 2000, 8
+    N = T * B * p
+    g2 = orc.build_g2(T, B, p, w)
+    rnd = random.Random(45)
+    for k, sign in ((0, 1), (N - 1, -1), (137, 1)):
+        Q = giant(w, k)
+        Ppt = Q if sign > 0 else pyec.neg(Q)                       # Px == Qx
+        dbl = pyec.add(Ppt, Ppt)
+        for planted in (True, False):
+            keys = synthetic_keys(w, [dbl[0]] + ([Ppt[0]] if planted else []) if planted else [], k)
+            cpu, gpu = orc.build_ht(keys, htsz)
+            exp = orc.launch(g2, T, B, p, gpu, htsz, Ppt)
+            if planted:
+                assert (4, k) in exp and (5, 0) in exp
+            with pkg.Engine(T, B, p, w, htsz) as e:
+                e.upload_giants(g2); e.upload_ht(gpu)
+                assert norm_hits(e.step(Ppt)) == norm_hits(exp)
+                other = random_point(rnd)
+                got = sorted((win, c, 0 if c == 5 else i) for c, i, win in e.step_multi([other, Ppt]))
+                ex2 = sorted((wi, c, 0 if c == 5 else i) for wi, pt in enumerate([other, Ppt]) for c, i in orc.launch(g2, T, B, p, gpu, htsz, pt))
+                assert got == ex2
+
+
+# ------------------------------------------------------------------ the reference's own kernel on the same inputs
+def _ref_available(orc):
+    return os.path.exists(orc.REF_LIB) and os.path.exists(orc.REF_CUBIN)
+
+
+@pytest.mark.parametrize("case", [(32, 4, 16, 4096, 10), (64, 20, 100, 60000, 14), (128, 2, 8, 5000, 4), (512, 8, 6, 30000, 13)])
+def test_reference_kernel_oracle_and_product_agree(pkg, orc, case):
+    if not _ref_available(orc):
+        pytest.skip("oracle/_ref not built (reference tree absent at build time)")
+    T, B, p, w, htsz = case
+    Ppt, plant, cpu, gpu, g2 = build_case(orc, T, B, p, w, htsz, seed=4242 + T)
+    ref = orc.RefKernel(T, B, p, w, htsz)
+    ref.upload(g2, gpu)
+    with pkg.Engine(T, B, p, w, htsz) as e:
+        e.upload_giants(g2); e.upload_ht(gpu)
+        rnd = random.Random(5)
+        for pt in [Ppt] + [random_point(rnd) for _ in range(2)]:
+            r_hits, r_count, _ = ref.launch(pt)
+            assert r_count <= 240
+            o_hits = norm_hits(orc.launch(g2, T, B, p, gpu, htsz, pt))
+            assert r_hits == o_hits                                   # oracle pinned by the reference's kernel
+            assert norm_hits(e.step(pt)) == r_hits                     # product == reference
+    ref.close()
+
+
+def test_reference_kernel_codes_4_5(pkg, orc):
+    if not _ref_available(orc):
+        pytest.skip("oracle/_ref not built")
+    T, B, p, w, htsz = 32, 4, 8, 2000, 8
+    N = T * B * p
+    g2 = orc.build_g2(T, B, p, w)
+    for k, sign in ((5, 1), (N - 1, -1)):
+        Q = giant(w, k)
+        Ppt = Q if sign > 0 else pyec.neg(Q)
+        dbl = pyec.add(Ppt, Ppt)
+        cpu, gpu = orc.build_ht(synthetic_keys(w, [dbl[0], Ppt[0]], k), htsz)
+        ref = orc.RefKernel(T, B, p, w, htsz); ref.upload(g2, gpu)
+        r_hits, _, _ = ref.launch(Ppt)
+        ref.close()
+        assert (4, k) in r_hits and (5, 0) in r_hits
+        assert r_hits == norm_hits(orc.launch(g2, T, B, p, gpu, htsz, Ppt))
+        with pkg.Engine(T, B, p, w, htsz) as e:
+            e.upload_giants(g2); e.upload_ht(gpu)
+            assert norm_hits(e.step(Ppt)) == r_hits
+
+
+# ------------------------------------------------------------------ whole problems
+def test_solve_small_range_true_tables(pkg, orc):
+    """Real baby table + giants (built by the oracle on the CPU), key recovered through bsgs_run."""
+    T, B, p, w, htsz = 32, 4, 8, 1 << 14, 12
+    keys = orc.baby_keys(w)
+    cpu, gpu = orc.build_ht(keys, htsz)
+    g2 = orc.build_g2(T, B, p, w)
+    rnd = random.Random(2026)
+    pk = 1 << 35
+    with pkg.Engine(T, B, p, w, htsz) as e:
+        e.upload_giants(g2); e.upload_ht(gpu)
+        for _ in range(6):
+            secret = pk + rnd.randrange(1, 1 << 34)
+            if (secret - pk - 1 - p * w) % (2 * w) == 0:
+                secret += 1
+            target = pyec.mul(pyec.G, secret)
+            key, done, seen = pkg.solve(e, cpu, T, B, p, w, htsz, pk, pk + (1 << 34), target, batch=4)
+            assert key == secret
+
+
+def test_run_equals_stepwise(pkg, orc):
+    T, B, p, w, htsz = 16, 4, 8, 5000, 9
+    rnd = random.Random(77)
+    s = pkg.Search(T, B, p, w, htsz, 12345, random_point(rnd))
+    pts = [s.window_point(j) for j in range(7)]
+    xs = [candidate_x(pts[j], w, (j * 53) % (T * B * p), 1 + (j & 1)) for j in range(7)]
+    cpu, gpu = orc.build_ht(synthetic_keys(w, xs, 3), htsz)
+    g2 = orc.build_g2(T, B, p, w)
+    with pkg.Engine(T, B, p, w, htsz) as e:
+        e.upload_giants(g2); e.upload_ht(gpu)
+        hits, done = e.run(s.P0, s.D, 7, batch=3)
+        assert done == 7
+        exp = sorted((j, c, 0 if c == 5 else i) for j in range(7) for c, i in orc.launch(g2, T, B, p, gpu, htsz, pts[j]))
+        assert sorted((win, c, 0 if c == 5 else i) for c, i, win in hits) == exp and len(exp) >= 7
+
+
+def test_error_behaviour(pkg):
+    with pytest.raises(pkg.BsgsError):
+        pkg.Engine(1 << 12, 1 << 12, 1 << 8, 1000, 10)              # N >= 2^31
+    with pkg.Engine(8, 2, 2, 100, 4) as e:
+        with pytest.raises(pkg.BsgsError):
+            e.step(pyec.G)                                            # tables not uploaded
+        with pytest.raises(pkg.BsgsError):
+            e.upload_ht(np.zeros(10, dtype=np.uint8))                 # wrong size
