@@ -1,0 +1,296 @@
+#!/usr/bin/env python3
+"""bench.py -- giant-steps/s of the BSGS giant-step hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's own kernel, same box
+
+A "step" is ONE launch of the hot path: `nwin` consecutive GetJob windows (1_9_7File.pb:2077-2092)
+against the resident giant array and baby-step table = nwin * 2*T*B*p giant steps (the reference
+counts 2*T*B*p per launch, 1_9_7File.pb:2371).  Workload at N=1 = BASELINE.json configs[1]:
+puzzle #65 public key, -t 512 -b 148 -p 256 -w 30 -htsz 28.  At N>1 each rank owns a disjoint
+contiguous sub-range of windows with the same per-GPU tables (weak scaling, no per-step collective;
+one NCCL broadcast of the htGPU image at start-up).
+
+Timing: device time with CUDA events on the launching stream (inside libbsgs_b200.so), bracketed by
+barrier + synchronize, max over ranks.  Inputs (5.4 GB table + 1.2 GB giants) are far larger than
+the 126 MB L2.  `e2e` goes through the reference-facing C-ABI call bsgs_run() with HOST buffers:
+base point and stride in host memory in, hit records in host memory out, every launch's parameter
+upload and record read-back inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PUZZLE65_PUB = "0230210c23b1a047bc9bdbb13448e67deddc108946de6de639bcc75d47c0216b1b"
+PUZZLE65_PK, PUZZLE65_PKE = 0x10000000000000000, 0x1ffffffffffffffff
+M32_PER_STEP = 256            # algorithmic 32x32->64 multiply-adds per giant step
+IMAD_FALLBACK_LANES = 64.0    # lanes/clk/SM if the micro-benchmark cannot run
+
+
+def workload(args):
+    if args.small:            # plumbing-sized variant for quick checks (not a bench line)
+        return dict(T=128, B=16, p=32, w=1 << 20, htsz=18, name="small (debug)")
+    return dict(T=512, B=148, p=256, w=1 << 30, htsz=28, name="configs[1]: puzzle#65, -t 512 -b 148 -p 256 -w 30 -htsz 28")
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
+        sm = sorted(int(float(r[0])) for r in rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in rows)]
+        pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(float(rows[0][1])) if rows else None,
+                "reasons": reasons, "samples": len(rows), "power_w_max": max(pw) if pw else None}
+
+
+def imad_peak(sm_mhz_max):
+    """Measured integer-MAD issue rate of this box (bsgs-cuda_b200/imad_peak); lanes/clk/SM."""
+    exe = os.path.join(ROOT, "bsgs-cuda_b200", "imad_peak")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+        j = json.loads(out)
+        return j, "measured (imad_peak on this box)"
+    except Exception as e:                                           # noqa: BLE001
+        return {"sms": 148, "imad_wide_u32": {"lanes_per_clk_per_sm": IMAD_FALLBACK_LANES}}, f"fallback ({type(e).__name__})"
+
+
+def dist_setup(args):
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+    return rank, world, local, dist
+
+
+class DevBuf:
+    """A device allocation owned by libbsgs_b200.so, viewed as a torch uint8 tensor (for NCCL)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def run_b200(args):
+    import torch
+    import bsgs_cuda_b200 as b
+    from bsgs_cuda_b200 import ec
+    rank, world, local, dist = dist_setup(args)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = workload(args)
+    T, B, p, w, htsz = wl["T"], wl["B"], wl["p"], wl["w"], wl["htsz"]
+    N = T * B * p
+    nwin = args.nwin
+    opts = dict(max_windows=max(nwin, 1), blocks_per_sm=args.blocks_per_sm, bucket_bytes=args.bucket_bytes)
+    e = b.Engine(T, B, p, w, htsz, device=local, **opts)
+    t_setup = time.time()
+    e.giants_generate()                                              # every rank: 0.1 s of GPU work, no point broadcasting
+    bcast = None
+    if world == 1:
+        e.ht_build_synthetic(seed=args.seed)
+    else:                                                            # rank 0 builds, one NCCL broadcast of the htGPU image
+        ptr, nbytes = e.ht_staging()
+        if rank == 0:
+            e.ht_build_synthetic(seed=args.seed)
+        buf = torch.as_tensor(DevBuf(ptr, nbytes), device=f"cuda:{local}")
+        torch.cuda.synchronize(); dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(); dist.broadcast(buf, src=0); ev1.record(); torch.cuda.synchronize()
+        bcast = {"bytes": nbytes, "ms": ev0.elapsed_time(ev1), "GBps": nbytes / ev0.elapsed_time(ev1) / 1e6}
+        if rank != 0:
+            e.ht_commit()
+    t_setup = time.time() - t_setup
+    info = e.info()
+
+    # windows: rank r owns the contiguous block of windows [r*Wr, (r+1)*Wr) of the 2^64 range
+    target = ec.parse_pubkey(PUZZLE65_PUB)
+    s = b.Search(T, B, p, w, htsz, PUZZLE65_PK, target)
+    total_windows = s.windows_needed(PUZZLE65_PKE)
+    per_rank = (total_windows + world - 1) // world
+    first = rank * per_rank
+    K, W = args.steps, max(args.warmup, 3)
+    pts = [s.window_point((first + j) % total_windows) for j in range((K + W) * nwin)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    e.time_launches(pts[:W * nwin], nwin, W)                         # warm-up
+    smp = ClockSampler(local); smp.start(); time.sleep(0.3)
+    barrier(); t0 = time.time()
+    ms = e.time_launches(pts[W * nwin:(W + K) * nwin], nwin, K)
+    barrier(); t1 = time.time()
+    clocks = smp.stop(t0, t1)
+    # ---- end to end through bsgs_run (host buffers in, host records out)
+    e.run(s.window_point(first), s.pubaddbig, W * nwin, batch=nwin)
+    barrier(); te0 = time.perf_counter()
+    hits, done = e.run(s.window_point(first), s.pubaddbig, K * nwin, batch=nwin)
+    torch.cuda.synchronize(); te = (time.perf_counter() - te0) * 1e3
+    barrier()
+    if world > 1:
+        tt = torch.tensor([ms, te], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, te = float(tt[0]), float(tt[1])
+    steps_per_launch = 2 * N * nwin
+    value = steps_per_launch * K * world / (ms * 1e-3)
+    e2e = steps_per_launch * K * world / (te * 1e-3)
+
+    line = None
+    if rank == 0:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        sm_max = (clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+        ip, ip_how = imad_peak(sm_max)
+        lanes = ip["imad_wide_u32"]["lanes_per_clk_per_sm"]
+        sms = ip.get("sms", 148)
+        peak_m32 = sms * lanes * sm_max * 1e6                        # M32/s at max clock
+        ach_m32 = value / world * M32_PER_STEP
+        load = w / (1 << htsz)
+        bytes_per_step = 8 + 4 * load + 32                           # probe (offset pair + tags) + giant stream
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line = {
+            "metric": "giant-steps/s", "value": value, "unit": "giant-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit Fp)",
+            "data": "synthetic: uniformly random 64-bit table keys (seed %d) in the htGPU layout; real giant array and real puzzle#65 base points" % args.seed,
+            "config": {"workload": wl["name"], "T": T, "B": B, "p": p, "w": w, "htsz": htsz, "windows_per_launch": nwin,
+                       "giant_steps_per_launch": steps_per_launch, "keys_per_giant_step": 2 * w, "l2": "inputs (6.6 GB) larger than L2",
+                       "grid": info["grid"], "block": info["block"], "points_per_thread": info["points_per_thread"],
+                       "bucket_bytes": args.bucket_bytes, "parallelism": f"{world} x disjoint window ranges"},
+            "keys_per_s": value * 2 * w,
+            "e2e": {"value": e2e, "unit": "giant-steps/s", "h2d_bytes_per_step": 128 * nwin, "d2h_bytes_per_step": 16 + 64 * 12,
+                    "api": "bsgs_run (C ABI, host buffers)", "ms_per_step": te / K},
+            "gpu_launches": K,
+            "roofline": {"bound": "imad", "achieved": ach_m32 / 1e12, "peak": peak_m32 / 1e12, "unit": "T mad32/s", "frac": ach_m32 / peak_m32,
+                         "traffic": None, "per_unit": f"{M32_PER_STEP} mad32 per giant step", "peak_source": ip_how,
+                         "imad_lanes_per_clk_per_sm": lanes, "sm_mhz_for_peak": sm_max},
+            "roofline_hbm": {"bound": "hbm", "achieved": value / world * bytes_per_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": value / world * bytes_per_step / 1e9 / hbm_peak, "per_unit": f"{bytes_per_step:.1f} B per giant step",
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            "clocks": clocks, "setup_s": t_setup, "hits_in_e2e": len(hits),
+        }
+        if bcast:
+            line["ht_broadcast"] = bcast
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(e, T, B, p, htsz, pts[:8])
+    e.close()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    return line
+
+
+def cpu_baseline(engine, T, B, p, htsz, pts, budget_s=12.0):
+    """The oracle port (C restatement of one launch, batch 4096 like #helpsize) on all host cores."""
+    from oracle import oracle as orc
+    orc.build(); orc.lib()
+    g2 = engine.giants_export(); ht = engine.ht_export("gpu")
+    cores = os.cpu_count() or 1
+    N = T * B * p
+    t0 = time.time(); steps = 0; launches = 0
+    while time.time() - t0 < budget_s:
+        orc.launch(g2, T, B, p, ht, htsz, pts[launches % len(pts)], batch=4096, nthreads=cores, cap=1 << 16)
+        steps += 2 * N; launches += 1
+    dt = time.time() - t0
+    return {"value": steps / dt, "unit": "giant-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{launches} full launches ({steps} giant steps) of the same workload in {dt:.1f} s, oracle/bsgs_oracle.c orc_launch"}
+
+
+def run_reference(args):
+    """The reference's OWN kernel (`_test1`, PTX embedded in 1_9_7File.pb:5181-23979, assembled for
+    sm_100a by oracle/Makefile) through oracle/ref_harness.c on the same B200; falls back to the CPU
+    oracle port when oracle/_ref was not built."""
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return None
+    import bsgs_cuda_b200 as b
+    from bsgs_cuda_b200 import ec
+    from oracle import oracle as orc
+    orc.build(); orc.lib()
+    wl = workload(args)
+    T, B, p, w, htsz = wl["T"], wl["B"], wl["p"], wl["w"], wl["htsz"]
+    N = T * B * p
+    K, W = args.steps, max(args.warmup, 3)
+    target = ec.parse_pubkey(PUZZLE65_PUB)
+    s = b.Search(T, B, p, w, htsz, PUZZLE65_PK, target)
+    pts = [s.window_point(j) for j in range(8)]
+    # same tables as the product arm (built with the product's table builders, which are parity-tested)
+    e = b.Engine(T, B, p, w, htsz, device=0)
+    e.giants_generate(); e.ht_build_synthetic(seed=args.seed)
+    cpu = cpu_baseline(e, T, B, p, htsz, pts, budget_s=10.0)
+    line = {"impl": "reference", "metric": "giant-steps/s", "unit": "giant-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit Fp)",
+            "config": {"workload": wl["name"], "T": T, "B": B, "p": p, "w": w, "htsz": htsz}, "cpu_baseline": cpu}
+    if os.path.exists(orc.REF_LIB) and os.path.exists(orc.REF_CUBIN):
+        ref = orc.RefKernel(T, B, p, w, htsz)
+        ref.upload_giants(e.giants_export())
+        ptr, nbytes = e.ht_device_image(); ref.upload_ht_dev(ptr, nbytes)
+        e.close()
+        ref.time_launches(pts[0], W)
+        ms = 0.0
+        for i in range(K):
+            ms += ref.time_launches(pts[i % len(pts)], 1)
+        value = 2 * N * K / (ms * 1e-3)
+        line.update({"value": value, "ms_per_step": ms / K, "gpu_launches": K,
+                     "reference_kind": "the reference's own GPU kernel _test1 (PTX from 1_9_7File.pb, ptxas -arch=sm_100a) on this box, 1 GPU; "
+                                       "the reference has no CPU giant-step loop, see cpu_baseline for the CPU restatement",
+                     "e2e": {"value": value, "unit": "giant-steps/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": 4}})
+        ref.close()
+    else:
+        e.close()
+        line.update({"value": cpu["value"], "ms_per_step": None, "gpu_launches": 0,
+                     "reference_kind": "oracle port on host cores (oracle/_ref not built)",
+                     "e2e": {"value": cpu["value"], "unit": "giant-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nwin", type=int, default=4, help="GetJob windows per launch")
+    ap.add_argument("--blocks-per-sm", type=int, default=2)
+    ap.add_argument("--bucket-bytes", type=int, default=32)
+    ap.add_argument("--seed", type=int, default=20261017)
+    ap.add_argument("--small", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    line = run_reference(args) if args.impl == "reference" else run_b200(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -2,6 +2,8 @@
 // reference interfaces each entry point replaces).
 #include "../../include/bsgs_b200.h"
 #include "giant_step.cuh"
+#include "table_build.cuh"
+#include "table_gen.cuh"
 #include "host_ec.h"
 #include <cuda_runtime.h>
 #include <new>
@@ -21,6 +23,7 @@ struct bsgs_ctx {
     uint4 *d_gx = nullptr, *d_gy = nullptr, *d_chain = nullptr;
     void* d_ht = nullptr;            // raw htGPU image: off[H+1] | tags[w]  (kept: CSR fallback)
     uint32_t* d_buckets = nullptr;
+    uint32_t* d_js = nullptr;        // payload j of every CSR item (htCPU image = tags interleaved with these)
     uint32_t* d_hits = nullptr;      // [0] counter, [4..] records (3 u32 each)
     unsigned long long* d_scratch = nullptr;
     uint32_t hit_cap = 1u << 16;
@@ -42,6 +45,7 @@ struct bsgs_ctx {
         }                                                                \
     } while (0)
 
+static int alloc_giants(bsgs_ctx* ctx);
 static size_t ht_image_bytes(const bsgs_ctx* c) { return (size_t)c->H * 4 + 4 + (size_t)c->w * 4; }
 
 extern "C" const char* bsgs_strerror(int s) {
@@ -97,7 +101,7 @@ extern "C" void bsgs_destroy(bsgs_ctx* ctx) {
     cudaSetDevice(ctx->dev);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_g2_stage); cudaFree(ctx->d_gx); cudaFree(ctx->d_gy); cudaFree(ctx->d_chain);
-    cudaFree(ctx->d_ht); cudaFree(ctx->d_buckets); cudaFree(ctx->d_hits); cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_ht); cudaFree(ctx->d_buckets); cudaFree(ctx->d_js); cudaFree(ctx->d_hits); cudaFree(ctx->d_scratch);
     if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
     if (ctx->e0) cudaEventDestroy(ctx->e0);
     if (ctx->e1) cudaEventDestroy(ctx->e1);
@@ -134,13 +138,7 @@ extern "C" int bsgs_giants_commit(bsgs_ctx* ctx) {
     if (!ctx || !ctx->d_g2_stage) return BSGS_E_STATE;
     CU(cudaSetDevice(ctx->dev));
     size_t slots = (size_t)ctx->NT * ctx->PP;
-    if (!ctx->d_gx) {
-        CU(cudaMalloc(&ctx->d_gx, slots * 32));
-        CU(cudaMalloc(&ctx->d_gy, slots * 32));
-        ctx->chain_bytes = slots * 32 * ctx->max_windows;
-        CU(cudaMalloc(&ctx->d_chain, ctx->chain_bytes));
-        ctx->giants_bytes = slots * 64;
-    }
+    { int rc = alloc_giants(ctx); if (rc) return rc; }
     uint32_t blocks = (uint32_t)((slots + 255) / 256);
     gs::k_convert_g2<<<blocks, 256, 0, ctx->stream>>>((const uint32_t*)ctx->d_g2_stage, ctx->d_gx, ctx->d_gy, ctx->T, ctx->B, ctx->p,
                                                      (uint32_t)ctx->N, ctx->NT, ctx->PP);
@@ -157,6 +155,58 @@ extern "C" int bsgs_upload_giants(bsgs_ctx* ctx, const void* g2, size_t bytes) {
     CU(cudaMemcpyAsync(d, g2, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return bsgs_giants_commit(ctx);
+}
+
+// ---- device-side giant array (replaces giant(0) + Writeint, F197:1418-1488, 1831-1903)
+static int alloc_giants(bsgs_ctx* ctx) {
+    size_t slots = (size_t)ctx->NT * ctx->PP;
+    if (!ctx->d_gx) {
+        CU(cudaMalloc(&ctx->d_gx, slots * 32));
+        CU(cudaMalloc(&ctx->d_gy, slots * 32));
+        ctx->chain_bytes = slots * 32 * ctx->max_windows;
+        CU(cudaMalloc(&ctx->d_chain, ctx->chain_bytes));
+        ctx->giants_bytes = slots * 64;
+    }
+    return BSGS_OK;
+}
+static void to_const(tgen::PtConst& c, const hec::Pt& p) { memcpy(c.x, p.x.v, 32); memcpy(c.y, p.y.v, 32); }
+extern "C" int bsgs_giants_generate(bsgs_ctx* ctx) {
+    if (!ctx) return BSGS_E_ARG;
+    CU(cudaSetDevice(ctx->dev));
+    int rc = alloc_giants(ctx);
+    if (rc) return rc;
+    hec::Pt A;                                                   // A = m*D, D = ADDPUBG = -(2w)G  (F197:4689-4698)
+    hec::pt_mul_u64(A, hec::kG, 2 * ctx->w);
+    hec::pt_neg(A, A);
+    tgen::PtConst c; to_const(c, A);
+    tgen::k_set_slot<<<1, 32, 0, ctx->stream>>>(ctx->d_gx, ctx->d_gy, ctx->NT, 0, c);
+    for (uint64_t m = 1; m < ctx->N; m *= 2) {
+        uint64_t cnt = m - 1 < ctx->N - m ? m - 1 : ctx->N - m;
+        if (cnt) tgen::k_giants_extend<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_gx, ctx->d_gy, ctx->NT, m, cnt, c);
+        hec::pt_add(A, A, A);                                    // (2m)*D = Q_{2m-1}
+        to_const(c, A);
+        if (2 * m - 1 < ctx->N) tgen::k_set_slot<<<1, 32, 0, ctx->stream>>>(ctx->d_gx, ctx->d_gy, ctx->NT, 2 * m - 1, c);
+    }
+    uint64_t total = (uint64_t)ctx->NT * ctx->PP;
+    if (total > ctx->N) tgen::k_pad_slots<<<(unsigned)((total - ctx->N + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_gx, ctx->d_gy, ctx->NT, ctx->N, total);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->giants_ready = true;
+    return BSGS_OK;
+}
+extern "C" int bsgs_giants_export(bsgs_ctx* ctx, void* g2, size_t bytes) {
+    if (!ctx || !g2 || bytes != (size_t)ctx->N * 64) return BSGS_E_ARG;
+    if (!ctx->giants_ready) return BSGS_E_STATE;
+    CU(cudaSetDevice(ctx->dev));
+    uint32_t* d = nullptr;
+    CU(cudaMalloc(&d, bytes));
+    tgen::k_export_g2<<<(unsigned)((ctx->N + 255) / 256), 256, 0, ctx->stream>>>(d, ctx->d_gx, ctx->d_gy, ctx->T, ctx->B, ctx->p, (uint32_t)ctx->N, ctx->NT);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g2, d, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    CU(e);
+    return BSGS_OK;
 }
 
 extern "C" int bsgs_ht_staging(bsgs_ctx* ctx, void** dev_ptr, size_t* bytes) {
@@ -190,7 +240,77 @@ extern "C" int bsgs_upload_ht(bsgs_ctx* ctx, const void* htgpu, size_t bytes) {
     if (rc) return rc;
     CU(cudaMemcpyAsync(d, htgpu, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_js) { cudaFree(ctx->d_js); ctx->d_js = nullptr; }   // payloads of a previous device build are stale
     return bsgs_ht_commit(ctx);
+}
+
+// ---- device-side table construction (replaces HashTableInsert + sortHashTable32bit + packHT*File,
+// F197:2555-2622, 2771-2820, 3232-3444, for tables that never have to exist on the host)
+static int build_from_device_keys(bsgs_ctx* ctx, const uint64_t* d_keys) {
+    void* d; size_t n; int rc = bsgs_ht_staging(ctx, &d, &n);
+    if (rc) return rc;
+    if (!ctx->d_js) CU(cudaMalloc(&ctx->d_js, (size_t)ctx->w * 4 + 16));
+    uint32_t* cursor = nullptr;
+    CU(cudaMalloc(&cursor, (size_t)ctx->H * 4));
+    uint32_t* off = (uint32_t*)ctx->d_ht;
+    cudaError_t e = tbl::build_csr(d_keys, ctx->w, ctx->H, off, off + ctx->H + 1, ctx->d_js, cursor, ctx->sm_count, ctx->stream);
+    cudaFree(cursor);
+    CU(e);
+    return bsgs_ht_commit(ctx);
+}
+extern "C" int bsgs_ht_build_from_keys(bsgs_ctx* ctx, const uint64_t* keys, uint64_t nkeys) {
+    if (!ctx || !keys || nkeys != ctx->w) return BSGS_E_ARG;
+    CU(cudaSetDevice(ctx->dev));
+    uint64_t* dk = nullptr;
+    CU(cudaMalloc(&dk, nkeys * 8));
+    cudaError_t e = cudaMemcpyAsync(dk, keys, nkeys * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    int rc = e == cudaSuccess ? build_from_device_keys(ctx, dk) : BSGS_E_CUDA;
+    if (e != cudaSuccess) { ctx->last_cuda = (int)e; cudaGetLastError(); }
+    cudaFree(dk);
+    return rc;
+}
+extern "C" int bsgs_ht_build_synthetic(bsgs_ctx* ctx, uint64_t seed) {
+    if (!ctx) return BSGS_E_ARG;
+    CU(cudaSetDevice(ctx->dev));
+    uint64_t* dk = nullptr;
+    CU(cudaMalloc(&dk, (size_t)ctx->w * 8));
+    tbl::k_fill_synth<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(dk, ctx->w, seed);
+    cudaError_t e = cudaGetLastError();
+    int rc = e == cudaSuccess ? build_from_device_keys(ctx, dk) : BSGS_E_CUDA;
+    if (e != cudaSuccess) { ctx->last_cuda = (int)e; cudaGetLastError(); }
+    cudaFree(dk);
+    return rc;
+}
+extern "C" int bsgs_ht_export(bsgs_ctx* ctx, int kind, void* out, size_t bytes) {
+    if (!ctx || !out) return BSGS_E_ARG;
+    if (!ctx->ht_ready) return BSGS_E_STATE;
+    CU(cudaSetDevice(ctx->dev));
+    size_t head = ((size_t)ctx->H + 1) * 4;
+    if (kind == 0) {                                             // htGPU image: the device buffer as it is
+        if (bytes != ht_image_bytes(ctx)) return BSGS_E_ARG;
+        CU(cudaMemcpyAsync(out, ctx->d_ht, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return BSGS_OK;
+    }
+    if (kind != 1 || bytes != head + (size_t)ctx->w * 8) return BSGS_E_ARG;
+    if (!ctx->d_js) return BSGS_E_STATE;                         // table was uploaded as htGPU: payloads unknown
+    uint2* items = nullptr;
+    CU(cudaMalloc(&items, (size_t)ctx->w * 8 + 16));
+    tbl::k_interleave<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const uint32_t*)ctx->d_ht + ctx->H + 1, ctx->d_js, items, ctx->w);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, ctx->d_ht, head, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t*)out + head, items, (size_t)ctx->w * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(items);
+    CU(e);
+    return BSGS_OK;
+}
+extern "C" int bsgs_ht_device_image(bsgs_ctx* ctx, void** dev_ptr, size_t* bytes) {
+    if (!ctx || !dev_ptr || !bytes) return BSGS_E_ARG;
+    if (!ctx->ht_ready) return BSGS_E_STATE;
+    *dev_ptr = ctx->d_ht; *bytes = ht_image_bytes(ctx);
+    return BSGS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ hot path
@@ -312,7 +432,7 @@ extern "C" int bsgs_time_launches(bsgs_ctx* ctx, uint32_t nwin, const uint8_t* p
     if (!ctx->giants_ready || !ctx->ht_ready) return BSGS_E_STATE;
     CU(cudaSetDevice(ctx->dev));
     CU(cudaEventRecord(ctx->e0, ctx->stream));
-    for (uint32_t i = 0; i < iters; i++) CU(launch_any(ctx, nwin, pxy_le));
+    for (uint32_t i = 0; i < iters; i++) CU(launch_any(ctx, nwin, pxy_le + (size_t)i * nwin * 64));
     CU(cudaEventRecord(ctx->e1, ctx->stream));
     CU(cudaEventSynchronize(ctx->e1));
     CU(cudaEventElapsedTime(ms, ctx->e0, ctx->e1));

@@ -89,4 +89,18 @@ static inline void pt_add(Pt& r, const Pt& a, const Pt& b) {
     r.x = x3; r.y = y3;
 }
 
+static const Pt kG = {{{0x59F2815B16F81798ULL, 0x029BFCDB2DCE28D9ULL, 0x55A06295CE870B07ULL, 0x79BE667EF9DCBBACULL}},
+                      {{0x9C47D08FFB10D4B8ULL, 0xFD17B448A6855419ULL, 0x5DA4FBFC0E1108A8ULL, 0x483ADA7726A3C465ULL}}};
+static inline void pt_neg(Pt& r, const Pt& a) { r.x = a.x; neg(r.y, a.y); }
+// k*a for 1 <= k < 2^64, LSB-first double-and-add like m_PTMULX64 (Curve64.pb:2586-2619)
+static inline void pt_mul_u64(Pt& r, const Pt& a, uint64_t k) {
+    Pt acc = a, res; bool have = false;
+    while (k) {
+        if (k & 1) { if (have) pt_add(res, res, acc); else { res = acc; have = true; } }
+        k >>= 1;
+        if (k) pt_add(acc, acc, acc);
+    }
+    r = res;
+}
+
 }  // namespace hec

@@ -30,6 +30,7 @@ class Info(C.Structure):
 
 EXPORTS = ["bsgs_create", "bsgs_destroy", "bsgs_strerror", "bsgs_last_cuda_error", "bsgs_upload_giants", "bsgs_upload_ht",
            "bsgs_giants_staging", "bsgs_giants_commit", "bsgs_ht_staging", "bsgs_ht_commit", "bsgs_step", "bsgs_step_multi",
+           "bsgs_giants_generate", "bsgs_giants_export", "bsgs_ht_build_from_keys", "bsgs_ht_build_synthetic", "bsgs_ht_export", "bsgs_ht_device_image",
            "bsgs_run", "bsgs_time_launches", "bsgs_probe_bench", "bsgs_probe_keys", "bsgs_get_info", "bsgs_set_option", "bsgs_debug_field"]
 
 _lib = None
@@ -56,6 +57,12 @@ def load():
     L.bsgs_giants_commit.argtypes = [vp]
     L.bsgs_ht_staging.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.bsgs_ht_commit.argtypes = [vp]
+    L.bsgs_giants_generate.argtypes = [vp]
+    L.bsgs_giants_export.argtypes = [vp, vp, C.c_size_t]
+    L.bsgs_ht_build_from_keys.argtypes = [vp, vp, u64]
+    L.bsgs_ht_build_synthetic.argtypes = [vp, u64]
+    L.bsgs_ht_export.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.bsgs_ht_device_image.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.bsgs_step.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(Hit), u32, C.POINTER(u32)]
     L.bsgs_step_multi.argtypes = [vp, u32, C.c_char_p, C.POINTER(Hit), u32, C.POINTER(u32)]
     L.bsgs_run.argtypes = [vp, C.c_char_p, C.c_char_p, u64, u32, u32, C.POINTER(Hit), u32, C.POINTER(u32), C.POINTER(u64)]
@@ -143,6 +150,33 @@ class Engine:
     def ht_commit(self):
         self._ck(self.L.bsgs_ht_commit(self.h), "bsgs_ht_commit")
 
+    def giants_generate(self):
+        self._ck(self.L.bsgs_giants_generate(self.h), "bsgs_giants_generate")
+
+    def giants_export(self) -> np.ndarray:
+        out = np.empty(self.N * 64, dtype=np.uint8)
+        self._ck(self.L.bsgs_giants_export(self.h, out.ctypes.data, out.nbytes), "bsgs_giants_export")
+        return out
+
+    def ht_build_from_keys(self, keys: np.ndarray):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        self._ck(self.L.bsgs_ht_build_from_keys(self.h, keys.ctypes.data, len(keys)), "bsgs_ht_build_from_keys")
+
+    def ht_build_synthetic(self, seed=1):
+        self._ck(self.L.bsgs_ht_build_synthetic(self.h, seed), "bsgs_ht_build_synthetic")
+
+    def ht_export(self, kind="gpu") -> np.ndarray:
+        H = 1 << self.htsz
+        n = 4 * H + 4 + self.w * (4 if kind == "gpu" else 8)
+        out = np.empty(n, dtype=np.uint8)
+        self._ck(self.L.bsgs_ht_export(self.h, 0 if kind == "gpu" else 1, out.ctypes.data, n), "bsgs_ht_export")
+        return out
+
+    def ht_device_image(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self.L.bsgs_ht_device_image(self.h, C.byref(p), C.byref(n)), "bsgs_ht_device_image")
+        return p.value, n.value
+
     # ---- hot path
     def _take(self, n):
         n = min(n, self.cap)
@@ -167,9 +201,11 @@ class Engine:
         return self._take(n.value), done.value
 
     # ---- measurement
-    def time_launches(self, points, iters):
+    def time_launches(self, points, nwin, iters):
+        """Device time (ms) of `iters` launches of `nwin` windows each; points holds iters*nwin base points."""
+        assert len(points) == nwin * iters
         ms = C.c_float()
-        self._ck(self.L.bsgs_time_launches(self.h, len(points), _pxy(points), iters, C.byref(ms)), "bsgs_time_launches")
+        self._ck(self.L.bsgs_time_launches(self.h, nwin, _pxy(points), iters, C.byref(ms)), "bsgs_time_launches")
         return ms.value
 
     def probe_bench(self, nkeys, seed=1, iters=1):

@@ -61,6 +61,10 @@ int  bsgs_last_cuda_error(const bsgs_ctx *ctx);            /* cudaError_t of the
 /* `g2` = the bytes of <T>_<B>_<p>_<w>_g2.BIN as they are (N*64 bytes; F197:1905-2058).
  * Replaces cuMemcpyHtoD of *GiantArrPacked (F197:2337). */
 int  bsgs_upload_giants(bsgs_ctx *ctx, const void *g2, size_t bytes);
+/* Device-side generation of the same array, Q_k = (k+1)*(-(2w)G) (replaces giant(0), F197:1418-1488,
+ * which is single-threaded on the CPU), and its export as the G2 file image (N*64 bytes). */
+int  bsgs_giants_generate(bsgs_ctx *ctx);
+int  bsgs_giants_export(bsgs_ctx *ctx, void *g2, size_t bytes);
 /* `htgpu` = the bytes of <Gx>_<w>_<H>_htGPUv0.BIN as they are (4H + 4 + 4w bytes; F197:3337-3444).
  * Replaces cuMemcpyHtoD of *GpuHT (F197:2350). */
 int  bsgs_upload_ht(bsgs_ctx *ctx, const void *htgpu, size_t bytes);
@@ -70,6 +74,19 @@ int  bsgs_giants_staging(bsgs_ctx *ctx, void **dev_ptr, size_t *bytes);
 int  bsgs_giants_commit(bsgs_ctx *ctx);
 int  bsgs_ht_staging(bsgs_ctx *ctx, void **dev_ptr, size_t *bytes);
 int  bsgs_ht_commit(bsgs_ctx *ctx);
+
+/* Device-side construction of the same table image (replaces HashTableInsert + sortHashTable32bit +
+ * packHTFile/packHTGPUFile, F197:2555-2622, 2771-2820, 3232-3444): counting sort of `nkeys` (= w)
+ * 64-bit keys, key j being the low 8 bytes of X((j+1)G) (F197:1127, 1221).  The resulting htGPU /
+ * htCPU images are byte-identical to the files the reference writes and can be exported. */
+int  bsgs_ht_build_from_keys(bsgs_ctx *ctx, const uint64_t *keys, uint64_t nkeys);
+/* measurement only: w uniformly random keys (splitmix64 of seed + j) instead of real baby steps */
+int  bsgs_ht_build_synthetic(bsgs_ctx *ctx, uint64_t seed);
+/* kind 0: htGPU file image (4H + 4 + 4w bytes); kind 1: htCPU file image (4H + 4 + 8w bytes; only
+ * after a device-side build, which knows the payloads j) */
+int  bsgs_ht_export(bsgs_ctx *ctx, int kind, void *out, size_t bytes);
+/* device address of the resident htGPU image (CSR form), e.g. as the source of a broadcast */
+int  bsgs_ht_device_image(bsgs_ctx *ctx, void **dev_ptr, size_t *bytes);
 
 /* -- the hot path -------------------------------------------------------------------------- */
 /* One reference launch: same base point, same (code, idx) multiset as `_test1` (order is not part
@@ -91,8 +108,9 @@ int  bsgs_run(bsgs_ctx *ctx, const uint8_t p0xy_le[64], const uint8_t dxy_le[64]
               uint64_t *windows_done);
 
 /* -- measurement helpers (used by bench.py; device-resident timing with CUDA events) -------- */
-/* `iters` back-to-back launches of nwin windows each on the context's stream; returns the elapsed
- * device time of the whole train in *ms (CUDA events on the launching stream). */
+/* `iters` back-to-back launches of nwin windows each on the context's stream (pxy_le holds
+ * iters*nwin base points, 64 bytes each); returns the elapsed device time of the whole train in *ms
+ * (CUDA events on the launching stream).  Hit records are discarded. */
 int  bsgs_time_launches(bsgs_ctx *ctx, uint32_t nwin, const uint8_t *pxy_le, uint32_t iters, float *ms);
 /* probe-only micro-kernel: nkeys pseudo-random 64-bit keys (splitmix64 of seed)
  * probed against the uploaded table; returns device ms and the number of keys that probed true. */

@@ -255,6 +255,8 @@ class RefKernel:
         self.L.ref_upload_ht.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         self.L.ref_launch.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         self.L.ref_destroy.argtypes = [C.c_void_p]
+        self.L.ref_upload_ht_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t]
+        self.L.ref_time_launches.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_float)]
         self.h = C.c_void_p()
         rc = self.L.ref_create(C.byref(self.h), dev, REF_CUBIN.encode(), T, B, p, w, htsz)
         if rc:
@@ -265,6 +267,20 @@ class RefKernel:
         assert rc == 0, rc
         rc = self.L.ref_upload_ht(self.h, htgpu.ctypes.data, htgpu.nbytes)
         assert rc == 0, rc
+
+    def upload_giants(self, g2: np.ndarray):
+        rc = self.L.ref_upload_giants(self.h, g2.ctypes.data, g2.nbytes)
+        assert rc == 0, rc
+
+    def upload_ht_dev(self, dev_ptr: int, nbytes: int):
+        rc = self.L.ref_upload_ht_dev(self.h, dev_ptr, nbytes)
+        assert rc == 0, rc
+
+    def time_launches(self, P_xy, iters: int) -> float:
+        ms = C.c_float()
+        rc = self.L.ref_time_launches(self.h, P_xy[0].to_bytes(32, "little"), P_xy[1].to_bytes(32, "little"), iters, C.byref(ms))
+        assert rc == 0, rc
+        return ms.value
 
     def launch(self, P_xy, cap=240):
         recs = (C.c_uint32 * (2 * cap))(); n = C.c_uint32(); ms = C.c_float()

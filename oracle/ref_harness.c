@@ -41,6 +41,7 @@ static struct {
     CUresult (*MemcpyHtoD)(CUdeviceptr, const void *, size_t);
     CUresult (*MemcpyDtoH)(void *, CUdeviceptr, size_t);
     CUresult (*MemsetD8)(CUdeviceptr, unsigned char, size_t);
+    CUresult (*MemcpyDtoD)(CUdeviceptr, CUdeviceptr, size_t);
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
     CUresult (*CtxSynchronize)(void);
     CUresult (*EventCreate)(CUevent *, unsigned);
@@ -63,7 +64,7 @@ static int load_cuda(void) {
     SYM(ModuleGetFunction, "cuModuleGetFunction"); SYM(ModuleGetGlobal, "cuModuleGetGlobal_v2");
     SYM(FuncSetCacheConfig, "cuFuncSetCacheConfig");
     SYM(MemAlloc, "cuMemAlloc_v2"); SYM(MemFree, "cuMemFree_v2");
-    SYM(MemcpyHtoD, "cuMemcpyHtoD_v2"); SYM(MemcpyDtoH, "cuMemcpyDtoH_v2"); SYM(MemsetD8, "cuMemsetD8_v2");
+    SYM(MemcpyHtoD, "cuMemcpyHtoD_v2"); SYM(MemcpyDtoH, "cuMemcpyDtoH_v2"); SYM(MemsetD8, "cuMemsetD8_v2"); SYM(MemcpyDtoD, "cuMemcpyDtoD_v2");
     SYM(LaunchKernel, "cuLaunchKernel"); SYM(CtxSynchronize, "cuCtxSynchronize");
     SYM(EventCreate, "cuEventCreate"); SYM(EventRecord, "cuEventRecord");
     SYM(EventSynchronize, "cuEventSynchronize"); SYM(EventElapsedTime, "cuEventElapsedTime");
@@ -139,6 +140,35 @@ int ref_upload_ht(ref_ctx *c, const void *htgpu, size_t bytes) {
     int rc = 0; if (bytes != c->H * 4 + 4 + c->w * 4) return -4;
     cu.CtxPush(c->ctx);
     CK(cu.MemcpyHtoD(c->base + c->puboffset, htgpu, bytes));   /* 1_9_7File.pb:2350 */
+out:
+    { CUcontext t; cu.CtxPop(&t); } return rc;
+}
+
+/* same image, already resident in device memory of the same (primary) context: device-to-device copy */
+int ref_upload_ht_dev(ref_ctx *c, unsigned long long dev_src, size_t bytes) {
+    int rc = 0; if (bytes != c->H * 4 + 4 + c->w * 4) return -4;
+    cu.CtxPush(c->ctx);
+    CK(cu.MemcpyDtoD(c->base + c->puboffset, (CUdeviceptr)dev_src, bytes));
+    CK(cu.CtxSynchronize());
+out:
+    { CUcontext t; cu.CtxPop(&t); } return rc;
+}
+
+/* timing only: `iters` back-to-back launches on the same base point, CUDA events around the train;
+ * the hit counter is cleared afterwards (records beyond 240 would run into the giants: callers use
+ * tables that yield few hits). */
+int ref_time_launches(ref_ctx *c, const uint8_t *px_le, const uint8_t *py_le, uint32_t iters, float *ms) {
+    int rc = 0; uint32_t words[16];
+    for (int i = 0; i < 8; i++) { memcpy(&words[i], px_le + 4 * (7 - i), 4); memcpy(&words[8 + i], py_le + 4 * (7 - i), 4); }
+    cu.CtxPush(c->ctx);
+    CK(cu.MemcpyHtoD(c->constA + 32, words, 64));
+    void *params[1] = {&c->base};
+    CK(cu.EventRecord(c->e0, 0));
+    for (uint32_t i = 0; i < iters; i++) CK(cu.LaunchKernel(c->fn, c->B, 1, 1, c->T, 1, 1, 0, 0, params, NULL));
+    CK(cu.EventRecord(c->e1, 0));
+    CK(cu.CtxSynchronize());
+    if (ms) cu.EventElapsedTime(ms, c->e0, c->e1);
+    { uint32_t z = 0; CK(cu.MemcpyHtoD(c->base, &z, 4)); }
 out:
     { CUcontext t; cu.CtxPop(&t); } return rc;
 }

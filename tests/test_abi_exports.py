@@ -1,0 +1,56 @@
+"""The C-ABI library loads on a machine without a GPU and exports every symbol include/*.h declares."""
+import ctypes
+import glob
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    names = []
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        src = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        names += re.findall(r"\b(bsgs_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_header_declares_the_boundary():
+    fns = declared_functions()
+    for must in ("bsgs_create", "bsgs_destroy", "bsgs_upload_giants", "bsgs_upload_ht", "bsgs_step", "bsgs_run", "bsgs_strerror"):
+        assert must in fns
+
+
+def test_library_exports_every_declared_symbol():
+    import bsgs_cuda_b200 as b
+    path = b.lib_path()
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "bsgs-cuda_b200"), "libbsgs_b200.so"])
+    lib = ctypes.CDLL(path)
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+    assert sorted(b.native.EXPORTS) == declared_functions()
+
+
+def test_no_compute_without_gpu_but_clean_errors():
+    """Without a device the library must return an error status, never crash or fall back."""
+    import bsgs_cuda_b200 as b
+    import torch
+    if torch.cuda.is_available():
+        return
+    L = b.native.load()
+    assert L.bsgs_strerror(0) == b"ok" and L.bsgs_strerror(-5) != b"ok"
+    try:
+        b.Engine(8, 2, 2, 100, 4)
+    except b.BsgsError as e:
+        assert e.status in (-2, -3)
+    else:
+        raise AssertionError("bsgs_create succeeded without a GPU")
+
+
+def test_product_never_imports_the_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "bsgs-cuda_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                assert "oracle" not in open(os.path.join(root, f), errors="replace").read().replace("CPU oracle", "").replace("oracle's", "").lower().replace("the oracle", ""), f

@@ -265,3 +265,41 @@ def test_error_behaviour(pkg):
             e.step(pyec.G)                                            # tables not uploaded
         with pytest.raises(pkg.BsgsError):
             e.upload_ht(np.zeros(10, dtype=np.uint8))                 # wrong size
+
+
+# ------------------------------------------------------------------ device-side table builders
+@pytest.mark.parametrize("T,B,p,w", [(32, 4, 16, 4096), (7, 3, 5, 1000), (64, 20, 100, 60000), (1, 1, 1, 5), (2, 1, 1, 9), (512, 8, 6, 1 << 30)])
+def test_giants_generate_equals_oracle_g2(pkg, orc, T, B, p, w):
+    with pkg.Engine(T, B, p, w, 10) as e:
+        e.giants_generate()
+        assert bytes(e.giants_export()) == bytes(orc.build_g2(T, B, p, w))
+
+
+def test_giants_upload_export_roundtrip(pkg, orc):
+    T, B, p, w = 24, 5, 7, 777
+    g2 = orc.build_g2(T, B, p, w)
+    with pkg.Engine(T, B, p, w, 8) as e:
+        e.upload_giants(g2)
+        assert bytes(e.giants_export()) == bytes(g2)
+
+
+@pytest.mark.parametrize("w,htsz", [(50000, 14), (50000, 9), (3000, 12), (1, 1), (100000, 4)])
+def test_ht_device_build_equals_oracle_images(pkg, orc, w, htsz):
+    keys = synthetic_keys(w, [], seed=w * 31 + htsz)
+    if w > 100:
+        keys[17] = keys[5]; keys[99] = keys[5]                      # duplicate (bucket, tag): later insert first
+    cpu, gpu = orc.build_ht(keys, htsz)
+    with pkg.Engine(4, 4, 4, w, htsz) as e:
+        e.ht_build_from_keys(keys)
+        assert bytes(e.ht_export("gpu")) == bytes(gpu)
+        assert bytes(e.ht_export("cpu")) == bytes(cpu)
+        assert e.probe_keys(keys[:2000]).all()
+
+
+def test_ht_true_baby_keys_device_build(pkg, orc):
+    w, htsz = 1 << 16, 13
+    keys = orc.baby_keys(w)
+    cpu, gpu = orc.build_ht(keys, htsz)
+    with pkg.Engine(4, 4, 4, w, htsz) as e:
+        e.ht_build_from_keys(keys)
+        assert bytes(e.ht_export("cpu")) == bytes(cpu)
