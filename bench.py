@@ -111,7 +111,7 @@ def run_b200(args):
     T, B, p, w, htsz = wl["T"], wl["B"], wl["p"], wl["w"], wl["htsz"]
     N = T * B * p
     nwin = args.nwin
-    opts = dict(max_windows=max(nwin, 1), blocks_per_sm=args.blocks_per_sm, bucket_bytes=args.bucket_bytes)
+    opts = dict(kernel=args.kernel, block=args.block, max_windows=max(nwin, 1), blocks_per_sm=args.blocks_per_sm, bucket_bytes=args.bucket_bytes)
     e = b.Engine(T, B, p, w, htsz, device=local, **opts)
     t_setup = time.time()
     e.giants_generate()                                              # every rank: 0.1 s of GPU work, no point broadcasting
@@ -283,6 +283,8 @@ def main():
     ap.add_argument("--nwin", type=int, default=4, help="GetJob windows per launch")
     ap.add_argument("--blocks-per-sm", type=int, default=2)
     ap.add_argument("--bucket-bytes", type=int, default=32)
+    ap.add_argument("--kernel", type=int, default=1)
+    ap.add_argument("--block", type=int, default=256)
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -331,3 +331,212 @@ __global__ void k_debug_field(int op, const uint32_t* a, const uint32_t* b, uint
 }
 
 }  // namespace gs
+
+// ================================================================================================
+// v2: compact-code kernel.  ncu on v1 (profiles/r1a) showed 36 % of all stall cycles in
+// "no instruction" (the fully inlined body of 7 field multiplications per window overflows the
+// instruction caches) and only 4 warps per scheduler at 126 registers.  Here the 256-bit
+// multiplication and squaring are real functions with register-passed operands, the window loop is
+// a run-time loop (window constants in shared memory), and probe keys go through a per-thread ring
+// in shared memory that is drained in bursts of independent sector loads, so that no probe state
+// is live across the arithmetic.
+// ================================================================================================
+namespace gs2 {
+
+using gs::Tables;
+using gs::WinConst;
+constexpr int kMaxW = 16;
+constexpr int kBlock = 256;
+constexpr int kRing = 16;                  // keys per thread between drains (2 per point-window)
+
+struct Fe { uint32_t v[8]; };
+struct WinParams { WinConst win[kMaxW]; };     // 2 KB of kernel parameters; rows: px | py | p - px | 2*py
+
+__device__ __noinline__ Fe mulf(Fe a, Fe b) { Fe r; fp::fe_mul(r.v, a.v, b.v); return r; }
+__device__ __noinline__ Fe sqrf(Fe a) { Fe r; fp::fe_sqr(r.v, a.v); return r; }
+
+// a^(p-2), 255 S + 15 M, through the two functions above (keeps the kernel's code small)
+__device__ __noinline__ Fe sqrnf(Fe a, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) a = sqrf(a);
+    return a;
+}
+__device__ __noinline__ Fe invf(Fe a) {
+    Fe x2 = mulf(sqrnf(a, 1), a);
+    Fe x3 = mulf(sqrnf(x2, 1), a);
+    Fe x6 = mulf(sqrnf(x3, 3), x3);
+    Fe x9 = mulf(sqrnf(x6, 3), x3);
+    Fe x11 = mulf(sqrnf(x9, 2), x2);
+    Fe x22 = mulf(sqrnf(x11, 11), x11);
+    Fe x44 = mulf(sqrnf(x22, 22), x22);
+    Fe x88 = mulf(sqrnf(x44, 44), x44);
+    Fe x176 = mulf(sqrnf(x88, 88), x88);
+    Fe x220 = mulf(sqrnf(x176, 44), x44);
+    Fe x223 = mulf(sqrnf(x220, 3), x3);
+    Fe t = mulf(sqrnf(x223, 23), x22);
+    t = mulf(sqrnf(t, 5), a);
+    t = mulf(sqrnf(t, 3), x2);
+    return mulf(sqrnf(t, 2), a);
+}
+
+__device__ __forceinline__ Fe ldg_fe(const uint4* p0, const uint4* p1) {
+    uint4 a = __ldg(p0), b = __ldg(p1);
+    Fe r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ Fe lds_fe(const uint32_t* s) {
+    uint4 a = *reinterpret_cast<const uint4*>(s), b = *reinterpret_cast<const uint4*>(s + 4);
+    Fe r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+
+template <int BW> struct Sector;
+template <> struct Sector<8> {
+    uint4 a, b;
+    __device__ __forceinline__ void load(const Tables& tb, uint32_t h) {
+        const uint4* p = reinterpret_cast<const uint4*>(tb.buckets) + 2ull * h;
+        a = __ldg(p); b = __ldg(p + 1);
+    }
+    __device__ __forceinline__ bool match(const Tables& tb, uint32_t h, uint32_t tag) const {
+        uint32_t meta = b.w;
+        uint32_t m = (a.x == tag ? 1u : 0u) | (a.y == tag ? 2u : 0u) | (a.z == tag ? 4u : 0u) | (a.w == tag ? 8u : 0u) |
+                     (b.x == tag ? 16u : 0u) | (b.y == tag ? 32u : 0u) | (b.z == tag ? 64u : 0u);
+        if (meta <= 7u) return (m & ((1u << meta) - 1u)) != 0u;
+        return gs::probe_csr(tb.csr_off, tb.csr_tags, h, tag);
+    }
+};
+template <> struct Sector<16> {
+    uint4 a, b, c, d;
+    __device__ __forceinline__ void load(const Tables& tb, uint32_t h) {
+        const uint4* p = reinterpret_cast<const uint4*>(tb.buckets) + 4ull * h;
+        a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); d = __ldg(p + 3);
+    }
+    __device__ __forceinline__ bool match(const Tables& tb, uint32_t h, uint32_t tag) const {
+        uint32_t meta = d.w;
+        uint32_t m = (a.x == tag ? 1u : 0u) | (a.y == tag ? 2u : 0u) | (a.z == tag ? 4u : 0u) | (a.w == tag ? 8u : 0u) |
+                     (b.x == tag ? 16u : 0u) | (b.y == tag ? 32u : 0u) | (b.z == tag ? 64u : 0u) | (b.w == tag ? 128u : 0u) |
+                     (c.x == tag ? 256u : 0u) | (c.y == tag ? 512u : 0u) | (c.z == tag ? 1024u : 0u) | (c.w == tag ? 2048u : 0u) |
+                     (d.x == tag ? 4096u : 0u) | (d.y == tag ? 8192u : 0u) | (d.z == tag ? 16384u : 0u);
+        if (meta <= 15u) return (m & ((1u << meta) - 1u)) != 0u;
+        return gs::probe_csr(tb.csr_off, tb.csr_tags, h, tag);
+    }
+};
+
+// Drain `cnt` (<= kRing, even) keys of this thread's ring.  Slot 2j / 2j+1 hold the minus / plus
+// key of the point-window with chain index ci0 - j (the unwind runs downwards); bit j of eqmask
+// marks a doubling (code 4, plus slot unused), bit j of deadmask a padding point.
+template <int BW>
+__device__ __noinline__ void drain(const Tables& tb, const uint64_t* ring, int cnt, int ci0, int W, uint32_t t,
+                                   uint32_t eqmask, uint32_t deadmask) {
+#pragma unroll 1
+    for (int s0 = 0; s0 < cnt; s0 += 4) {
+        Sector<BW> sec[4]; uint64_t key[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (s0 + j >= cnt) continue;
+            key[j] = ring[(s0 + j) * kBlock];
+            sec[j].load(tb, (uint32_t)key[j] & tb.mask);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int pair = (s0 + j) >> 1; bool plus = (s0 + j) & 1;
+            bool eq = (eqmask >> pair) & 1u, dead = (deadmask >> pair) & 1u;
+            if (s0 + j >= cnt || dead || (plus && eq)) continue;
+            if (sec[j].match(tb, (uint32_t)key[j] & tb.mask, (uint32_t)(key[j] >> 32))) {
+                int ci = ci0 - pair, r = ci / W, w = ci - r * W;
+                gs::record_hit(tb, plus ? 1u : (eq ? 4u : 2u), (uint32_t)r * tb.NT + t, (uint32_t)w);
+            }
+        }
+    }
+}
+
+template <int BW, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
+k_giant_step2(const Tables tb, const __grid_constant__ WinParams wp, int W) {
+    __shared__ __align__(16) uint32_t s_win[kMaxW * 32];
+    __shared__ uint64_t s_ring[kRing * kBlock];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t NT = tb.NT;
+    const int PP = (int)tb.PP;
+    for (int i = threadIdx.x; i < W * 32; i += kBlock) s_win[i] = reinterpret_cast<const uint32_t*>(&wp)[i];
+    __syncthreads();
+    uint64_t* ring = s_ring + threadIdx.x;
+
+    // code 5: the base point itself (thread 0 of the grid; PTX197:L49-109)
+    if (t == 0) {
+#pragma unroll 1
+        for (int w = 0; w < W; w++) {
+            uint64_t key = ((uint64_t)s_win[w * 32 + 1] << 32) | s_win[w * 32];
+            Sector<BW> sec; sec.load(tb, (uint32_t)key & tb.mask);
+            if (sec.match(tb, (uint32_t)key & tb.mask, (uint32_t)(key >> 32))) gs::record_hit(tb, 5u, 0u, (uint32_t)w);
+        }
+    }
+
+    // ---------------- PASS 1: running product of the denominators -> chain ----------------
+    Fe acc; acc.v[0] = 1;
+#pragma unroll
+    for (int i = 1; i < 8; i++) acc.v[i] = 0;
+#pragma unroll 1
+    for (int r = 0; r < PP; r++) {
+        Fe qx = ldg_fe(tb.gx + (size_t)(2 * r) * NT + t, tb.gx + (size_t)(2 * r + 1) * NT + t);
+#pragma unroll 1
+        for (int w = 0; w < W; w++) {
+            Fe px = lds_fe(s_win + w * 32), d;
+            fp::fe_sub_canon(d.v, px.v, qx.v);
+            if (fp::fe_is_zero(d.v)) d = lds_fe(s_win + w * 32 + 24);          // 2*Py
+            acc = mulf(acc, d);
+            size_t ci = (size_t)(r * W + w) * 2 * NT + t;
+            gs::st8_stream(tb.chain + ci, tb.chain + ci + NT, acc.v);
+        }
+    }
+
+    // ---------------- one inversion per thread ----------------
+    Fe inv = invf(acc);
+
+    // ---------------- PASS 2: unwind, slopes, X, keys -> ring -> probe bursts ----------------
+    int fill = 0, ci_first = 0; uint32_t eqmask = 0, deadmask = 0;
+#pragma unroll 1
+    for (int r = PP - 1; r >= 0; r--) {
+        const bool live = (uint32_t)r * NT + t < tb.N;
+#pragma unroll 1
+        for (int w = W - 1; w >= 0; w--) {
+            const int ci = r * W + w;
+            Fe qx = ldg_fe(tb.gx + (size_t)(2 * r) * NT + t, tb.gx + (size_t)(2 * r + 1) * NT + t);
+            Fe invd = inv;
+            Fe d;
+            { Fe px = lds_fe(s_win + w * 32); fp::fe_sub_canon(d.v, px.v, qx.v); }
+            const bool eq = fp::fe_is_zero(d.v);
+            if (eq) d = lds_fe(s_win + w * 32 + 24);
+            if (ci > 0) {
+                size_t cp = (size_t)(ci - 1) * 2 * NT + t;
+                Fe cprev; gs::ld8_stream(cprev.v, tb.chain + cp, tb.chain + cp + NT);
+                invd = mulf(inv, cprev);
+                inv = mulf(inv, d);
+            }
+            uint64_t keym, keyp = 0;
+            if (!eq) {
+                Fe qy = ldg_fe(tb.gy + (size_t)(2 * r) * NT + t, tb.gy + (size_t)(2 * r + 1) * NT + t);
+                Fe py = lds_fe(s_win + w * 32 + 8), u, s;
+                { Fe npx = lds_fe(s_win + w * 32 + 16); fp::fe_sub_canon(u.v, npx.v, qx.v); }     // -(Px + Qx)
+                fp::fe_add_lazy(s.v, py.v, qy.v);                                                  // P - Q  (code 2)
+                Fe l2 = sqrf(mulf(s, invd));
+                keym = fp::fe_add_low64_canon(l2.v, u.v);
+                fp::fe_sub_canon(s.v, py.v, qy.v);                                                 // P + Q  (code 1)
+                l2 = sqrf(mulf(s, invd));
+                keyp = fp::fe_add_low64_canon(l2.v, u.v);
+            } else {
+                Fe px = lds_fe(s_win + w * 32);
+                keym = gs::double_x_low64(px.v, invd.v);                                           // X(2P)  (code 4)
+            }
+            if (fill == 0) ci_first = ci;
+            ring[fill * kBlock] = keym; ring[(fill + 1) * kBlock] = keyp;
+            eqmask |= (eq ? 1u : 0u) << (fill >> 1);
+            deadmask |= (live ? 0u : 1u) << (fill >> 1);
+            fill += 2;
+            if (fill == kRing) { drain<BW>(tb, ring, fill, ci_first, W, t, eqmask, deadmask); fill = 0; eqmask = 0; deadmask = 0; }
+        }
+    }
+    if (fill) drain<BW>(tb, ring, fill, ci_first, W, t, eqmask, deadmask);
+}
+
+}  // namespace gs2

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-MAX_WINDOWS = 8
+MAX_WINDOWS = 16
 
 
 def lib_path() -> str:
@@ -115,6 +115,8 @@ class Engine:
         if rc:
             self.h = C.c_void_p()
             raise BsgsError(rc, "bsgs_create")
+        if "kernel" not in options and os.environ.get("BSGS_KERNEL"):
+            options["kernel"] = int(os.environ["BSGS_KERNEL"])
         for k, v in options.items():
             self._ck(self.L.bsgs_set_option(self.h, k.encode(), int(v)), f"bsgs_set_option({k})")
         self.cap = 1 << 16

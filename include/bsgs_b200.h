@@ -97,7 +97,7 @@ int  bsgs_step(bsgs_ctx *ctx, const uint8_t px_le[32], const uint8_t py_le[32],
 /* nwin (1..BSGS_MAX_WINDOWS) consecutive GetJob() windows in ONE launch: pxy_le holds nwin records
  * of 64 bytes (x then y).  Each giant point is loaded once for all windows and one field inversion
  * per thread is shared by all of them.  hits carry the window index. */
-#define BSGS_MAX_WINDOWS 8
+#define BSGS_MAX_WINDOWS 16
 int  bsgs_step_multi(bsgs_ctx *ctx, uint32_t nwin, const uint8_t *pxy_le,
                      bsgs_hit *out, uint32_t cap, uint32_t *nhits);
 /* Whole search loop on the library side: windows j = 0..nwindows-1 with base points

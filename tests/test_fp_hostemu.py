@@ -1,0 +1,80 @@
+"""The limb arithmetic of bsgs-cuda_b200/csrc/fp.cuh, compiled for the HOST with the PTX carry
+primitives emulated (csrc/fp_hostemu.cpp), against Python big ints.  CPU-only check of the exact
+code the kernel runs; the same cases run on the device in tests/test_gpu_parity.py."""
+import ctypes as C
+import os
+import random
+import subprocess
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = 2**256 - 2**32 - 977
+M64 = 2**64 - 1
+
+
+@pytest.fixture(scope="module")
+def he():
+    d = os.path.join(ROOT, "bsgs-cuda_b200")
+    subprocess.check_call(["make", "-C", d, "libfp_hostemu.so"], stdout=subprocess.DEVNULL)
+    return C.CDLL(os.path.join(d, "libfp_hostemu.so"))
+
+
+def limbs(x):
+    return (C.c_uint32 * 8)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+
+
+def val(a):
+    return sum(int(a[i]) << (32 * i) for i in range(8))
+
+
+EDGE = [0, 1, 2, P - 1, P, P + 1, 2**256 - 1, 2**256 - 2, 2**255, 977, 2**32 + 977, 2**224 - 1,
+        (2**256 - 1) ^ (2**64 - 1), 2**256 - 2**96, 2**256 - 2**32 - 978, P - 977]
+
+
+def test_mul_sqr_lazy_inputs(he):
+    rnd = random.Random(1)
+    vals = EDGE + [rnd.getrandbits(256) for _ in range(400)]
+    for a in vals:
+        b = vals[rnd.randrange(len(vals))]
+        r = limbs(0)
+        he.he_mul(r, limbs(a), limbs(b)); assert val(r) % P == a * b % P
+        he.he_sqr(r, limbs(a)); assert val(r) % P == a * a % P
+    for a in EDGE:                                      # all edge pairs
+        for b in EDGE:
+            r = limbs(0); he.he_mul(r, limbs(a), limbs(b)); assert val(r) % P == a * b % P
+
+
+def test_sub_add_canon(he):
+    rnd = random.Random(2)
+    vals = [v % P for v in EDGE] + [rnd.randrange(P) for _ in range(400)]
+    for a in vals:
+        b = vals[rnd.randrange(len(vals))]
+        r = limbs(0)
+        he.he_sub_canon(r, limbs(a), limbs(b)); assert val(r) == (a - b) % P
+        he.he_add_lazy(r, limbs(a), limbs(b)); assert val(r) < 2**256 and val(r) % P == (a + b) % P
+    for a in EDGE:
+        r = limbs(a); he.he_canon(r)
+        if a < 2 * P:
+            assert val(r) == a % P
+
+
+def test_inverse_chain(he):
+    rnd = random.Random(3)
+    for a in [1, 2, P - 1, 977] + [rnd.randrange(1, P) for _ in range(20)]:
+        r = limbs(0); he.he_inv(r, limbs(a)); assert val(r) % P == pow(a, P - 2, P)
+    r = limbs(5); he.he_inv(r, limbs(0)); assert val(r) % P == 0      # inv(0) = 0 like m_Ecc_modInvX64 (Curve64.pb:2475-2477)
+
+
+def test_low64_of_canonical_sum(he):
+    he.he_add_low64_canon.restype = C.c_uint64
+    rnd = random.Random(4)
+    hi = (2**256 - 1) ^ (2**96 - 1)
+    cases = []
+    for _ in range(300):
+        cases.append((rnd.getrandbits(256), rnd.randrange(P)))
+        cases.append((hi | rnd.getrandbits(96), rnd.randrange(P)))                 # exact slow path
+        cases.append((rnd.getrandbits(256), P - 1 - rnd.getrandbits(40)))
+        cases.append((2**256 - 1 - rnd.getrandbits(34), P - 1 - rnd.getrandbits(34)))
+    cases += [(a, u % P) for a in EDGE for u in EDGE]
+    for a, u in cases:
+        assert he.he_add_low64_canon(limbs(a), limbs(u)) == ((a + u) % P) & M64, (hex(a), hex(u))
