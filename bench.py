@@ -111,7 +111,7 @@ def run_b200(args):
     T, B, p, w, htsz = wl["T"], wl["B"], wl["p"], wl["w"], wl["htsz"]
     N = T * B * p
     nwin = args.nwin
-    opts = dict(kernel=args.kernel, block=args.block, max_windows=max(nwin, 1), blocks_per_sm=args.blocks_per_sm, bucket_bytes=args.bucket_bytes)
+    opts = dict(max_windows=max(nwin, 1), blocks_per_sm=args.blocks_per_sm)
     e = b.Engine(T, B, p, w, htsz, device=local, **opts)
     t_setup = time.time()
     e.giants_generate()                                              # every rank: 0.1 s of GPU work, no point broadcasting
@@ -187,7 +187,7 @@ def run_b200(args):
             "config": {"workload": wl["name"], "T": T, "B": B, "p": p, "w": w, "htsz": htsz, "windows_per_launch": nwin,
                        "giant_steps_per_launch": steps_per_launch, "keys_per_giant_step": 2 * w, "l2": "inputs (6.6 GB) larger than L2",
                        "grid": info["grid"], "block": info["block"], "points_per_thread": info["points_per_thread"],
-                       "bucket_bytes": args.bucket_bytes, "parallelism": f"{world} x disjoint window ranges"},
+                       "parallelism": f"{world} x disjoint window ranges"},
             "keys_per_s": value * 2 * w,
             "e2e": {"value": e2e, "unit": "giant-steps/s", "h2d_bytes_per_step": 128 * nwin, "d2h_bytes_per_step": 16 + 64 * 12,
                     "api": "bsgs_run (C ABI, host buffers)", "ms_per_step": te / K},
@@ -280,11 +280,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nwin", type=int, default=4, help="GetJob windows per launch")
-    ap.add_argument("--blocks-per-sm", type=int, default=2)
-    ap.add_argument("--bucket-bytes", type=int, default=32)
-    ap.add_argument("--kernel", type=int, default=1)
-    ap.add_argument("--block", type=int, default=256)
+    ap.add_argument("--nwin", type=int, default=16, help="GetJob windows per launch")
+    ap.add_argument("--blocks-per-sm", type=int, default=3)
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

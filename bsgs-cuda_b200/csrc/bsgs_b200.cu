@@ -2,7 +2,6 @@
 // reference interfaces each entry point replaces).
 #include "../../include/bsgs_b200.h"
 #include "giant_step.cuh"
-#include "giant_step3.cuh"
 #include "table_build.cuh"
 #include "table_gen.cuh"
 #include "host_ec.h"
@@ -18,7 +17,7 @@ struct bsgs_ctx {
     uint32_t T = 0, B = 0, p = 0, htsz = 0;
     uint64_t w = 0, N = 0, H = 0;
     // geometry
-    uint32_t blocks_per_sm = 2, grid = 0, NT = 0, PP = 0, max_windows = 4, bucket_words = 8, kernel = 1, block = 256;
+    uint32_t blocks_per_sm = 3, grid = 0, NT = 0, PP = 0, max_windows = 16, block = 256;
     // device memory
     void* d_g2_stage = nullptr;      // raw G2 image (freed after commit)
     uint4 *d_gx = nullptr, *d_gy = nullptr, *d_chain = nullptr;
@@ -113,11 +112,12 @@ extern "C" void bsgs_destroy(bsgs_ctx* ctx) {
 extern "C" int bsgs_set_option(bsgs_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return BSGS_E_ARG;
     if (ctx->d_gx || ctx->d_buckets) return BSGS_E_STATE;       // geometry is baked into the layouts
-    if (!strcmp(name, "blocks_per_sm")) { if (value < 1 || value > 8) return BSGS_E_ARG; ctx->blocks_per_sm = (uint32_t)value; compute_geometry(ctx); return BSGS_OK; }
-    if (!strcmp(name, "bucket_bytes")) { if (value != 32 && value != 64) return BSGS_E_ARG; ctx->bucket_words = (uint32_t)(value / 4); return BSGS_OK; }
+    if (!strcmp(name, "blocks_per_sm")) { if (value < 1 || value > 3) return BSGS_E_ARG; ctx->blocks_per_sm = (uint32_t)value; compute_geometry(ctx); return BSGS_OK; }
     if (!strcmp(name, "max_windows")) { if (value < 1 || value > BSGS_MAX_WINDOWS) return BSGS_E_ARG; ctx->max_windows = (uint32_t)value; return BSGS_OK; }
-    if (!strcmp(name, "kernel")) { if (value < 1 || value > 3) return BSGS_E_ARG; ctx->kernel = (uint32_t)value; if (value != 3) ctx->block = 256; compute_geometry(ctx); return BSGS_OK; }
-    if (!strcmp(name, "block")) { if ((value != 128 && value != 256) || (ctx->kernel != 3 && value != 256)) return BSGS_E_ARG; ctx->block = (uint32_t)value; compute_geometry(ctx); return BSGS_OK; }
+    if (!strcmp(name, "l2_fetch")) {                            // device-wide: DRAM->L2 fetch granularity for the random sector reads
+        if (value != 32 && value != 64 && value != 128) return BSGS_E_ARG;
+        CU(cudaSetDevice(ctx->dev)); CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value)); return BSGS_OK;
+    }
     return BSGS_E_ARG;
 }
 
@@ -221,17 +221,14 @@ extern "C" int bsgs_ht_staging(bsgs_ctx* ctx, void** dev_ptr, size_t* bytes) {
 extern "C" int bsgs_ht_commit(bsgs_ctx* ctx) {
     if (!ctx || !ctx->d_ht) return BSGS_E_STATE;
     CU(cudaSetDevice(ctx->dev));
-    if (ctx->kernel == 3) ctx->bucket_words = 8;                 // fingerprint sectors are always 32 bytes
-    size_t bbytes = (size_t)ctx->H * ctx->bucket_words * 4;
+    size_t bbytes = (size_t)ctx->H * 32;                         // one 32-byte fingerprint sector per bucket
     if (!ctx->d_buckets) CU(cudaMalloc(&ctx->d_buckets, bbytes));
     ctx->table_bytes = bbytes + ht_image_bytes(ctx);
     const uint32_t* off = (const uint32_t*)ctx->d_ht;
     const uint32_t* tags = off + ctx->H + 1;
     CU(cudaMemsetAsync(ctx->d_scratch, 0, 8, ctx->stream));
     uint32_t blocks = (uint32_t)((ctx->H + 255) / 256);
-    if (ctx->kernel == 3) gs3::k_build_fp_sectors<<<blocks, 256, 0, ctx->stream>>>(off, tags, (uint4*)ctx->d_buckets, ctx->H, ctx->d_scratch);
-    else if (ctx->bucket_words == 8) gs::k_build_buckets<8><<<blocks, 256, 0, ctx->stream>>>(off, tags, ctx->d_buckets, ctx->H, ctx->d_scratch);
-    else gs::k_build_buckets<16><<<blocks, 256, 0, ctx->stream>>>(off, tags, ctx->d_buckets, ctx->H, ctx->d_scratch);
+    gs::k_build_fp_sectors<<<blocks, 256, 0, ctx->stream>>>(off, tags, (uint4*)ctx->d_buckets, ctx->H, ctx->d_scratch);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(&ctx->overfull, ctx->d_scratch, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -334,68 +331,22 @@ static void fill_win(gs::WinConst& wc, const uint8_t* pxy) {
     memcpy(wc.px, x.v, 32); memcpy(wc.py, y.v, 32); memcpy(wc.npx, nx.v, 32); memcpy(wc.py2, y2.v, 32);
 }
 
-template <int W>
-static cudaError_t launch_w(const bsgs_ctx* c, const uint8_t* pxy) {
-    gs::StepParams<W> sp;
-    for (int i = 0; i < W; i++) fill_win(sp.win[i], pxy + 64 * i);
-    gs::Tables tb = make_tables(c);
-    if (c->bucket_words == 8) gs::k_giant_step<W, 8><<<c->grid, gs::kBlock, 0, c->stream>>>(tb, sp);
-    else gs::k_giant_step<W, 16><<<c->grid, gs::kBlock, 0, c->stream>>>(tb, sp);
-    return cudaGetLastError();
-}
-template <int MINB>
-static cudaError_t launch_v2(const bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
-    gs2::WinParams wp;
-    memset(&wp, 0, sizeof wp);
-    for (uint32_t i = 0; i < nwin; i++) fill_win(wp.win[i], pxy + 64 * i);
-    gs::Tables tb = make_tables(c);
-    if (c->bucket_words == 8) gs2::k_giant_step2<8, MINB><<<c->grid, gs2::kBlock, 0, c->stream>>>(tb, wp, (int)nwin);
-    else gs2::k_giant_step2<16, MINB><<<c->grid, gs2::kBlock, 0, c->stream>>>(tb, wp, (int)nwin);
-    return cudaGetLastError();
-}
 template <int BLOCK, int MINB>
-static cudaError_t launch_v3(const bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
-    gs3::WinParams wp;
+static cudaError_t launch_k(const bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
+    gs::WinParams wp;
     memset(&wp, 0, sizeof wp);
     for (uint32_t i = 0; i < nwin; i++) fill_win(wp.win[i], pxy + 64 * i);
     gs::Tables tb = make_tables(c);
-    gs3::k_giant_step3<BLOCK, MINB><<<c->grid, BLOCK, 0, c->stream>>>(tb, wp, (int)nwin);
+    gs::k_giant_step<BLOCK, MINB><<<c->grid, BLOCK, 0, c->stream>>>(tb, wp, (int)nwin);
     return cudaGetLastError();
 }
 static cudaError_t launch_any(const bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
-    if (c->kernel == 3) {
-        switch (c->block * 16 + c->blocks_per_sm) {
-            case 256 * 16 + 1: case 256 * 16 + 2: return launch_v3<256, 2>(c, nwin, pxy);
-            case 256 * 16 + 3: return launch_v3<256, 3>(c, nwin, pxy);
-            case 256 * 16 + 4: return launch_v3<256, 4>(c, nwin, pxy);
-            case 128 * 16 + 4: return launch_v3<128, 4>(c, nwin, pxy);
-            case 128 * 16 + 5: return launch_v3<128, 5>(c, nwin, pxy);
-            case 128 * 16 + 6: return launch_v3<128, 6>(c, nwin, pxy);
-            case 128 * 16 + 7: return launch_v3<128, 7>(c, nwin, pxy);
-            case 128 * 16 + 8: return launch_v3<128, 8>(c, nwin, pxy);
-            default: return cudaErrorInvalidValue;
-        }
+    if (nwin < 1 || nwin > BSGS_MAX_WINDOWS) return cudaErrorInvalidValue;
+    switch (c->blocks_per_sm) {
+        case 1: case 2: return launch_k<256, 2>(c, nwin, pxy);
+        case 3: return launch_k<256, 3>(c, nwin, pxy);
+        default: return cudaErrorInvalidValue;
     }
-    if (c->kernel == 2) {
-        switch (c->blocks_per_sm) {
-            case 2: return launch_v2<2>(c, nwin, pxy);
-            case 3: return launch_v2<3>(c, nwin, pxy);
-            case 4: return launch_v2<4>(c, nwin, pxy);
-            default: return cudaErrorInvalidValue;
-        }
-    }
-    if (nwin > 8) return cudaErrorInvalidValue;
-    switch (nwin) {
-        case 1: return launch_w<1>(c, pxy);
-        case 2: return launch_w<2>(c, pxy);
-        case 3: return launch_w<3>(c, pxy);
-        case 4: return launch_w<4>(c, pxy);
-        case 5: return launch_w<5>(c, pxy);
-        case 6: return launch_w<6>(c, pxy);
-        case 7: return launch_w<7>(c, pxy);
-        case 8: return launch_w<8>(c, pxy);
-    }
-    return cudaErrorInvalidValue;
 }
 
 // read back counter + records, clear the counter; appends to out[*nhits...] with window offset
@@ -495,9 +446,7 @@ extern "C" int bsgs_probe_bench(bsgs_ctx* ctx, uint64_t nkeys, uint64_t seed, ui
     uint32_t grid = (uint32_t)ctx->sm_count * 8;
     CU(cudaEventRecord(ctx->e0, ctx->stream));
     for (uint32_t i = 0; i < iters; i++) {
-        if (ctx->kernel == 3) gs3::k_probe_bench_fp<<<grid, 256, 0, ctx->stream>>>(tb, nkeys, seed + i * nkeys, ctx->d_scratch);
-        else if (ctx->bucket_words == 8) gs::k_probe_bench<8><<<grid, 256, 0, ctx->stream>>>(tb, nkeys, seed + i * nkeys, ctx->d_scratch);
-        else gs::k_probe_bench<16><<<grid, 256, 0, ctx->stream>>>(tb, nkeys, seed + i * nkeys, ctx->d_scratch);
+        gs::k_probe_bench_fp<<<grid, 256, 0, ctx->stream>>>(tb, nkeys, seed + i * nkeys, ctx->d_scratch);
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->e1, ctx->stream));
@@ -523,9 +472,7 @@ extern "C" int bsgs_probe_keys(bsgs_ctx* ctx, const uint64_t* keys, uint64_t nke
     e = cudaMemcpyAsync(dk, keys, nkeys * 8, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         uint32_t blocks = (uint32_t)((nkeys + 255) / 256);
-        if (ctx->kernel == 3) gs3::k_probe_keys_fp<<<blocks, 256, 0, ctx->stream>>>(tb, dk, nkeys, df);
-        else if (ctx->bucket_words == 8) gs::k_probe_keys<8><<<blocks, 256, 0, ctx->stream>>>(tb, dk, nkeys, df);
-        else gs::k_probe_keys<16><<<blocks, 256, 0, ctx->stream>>>(tb, dk, nkeys, df);
+        gs::k_probe_keys_fp<<<blocks, 256, 0, ctx->stream>>>(tb, dk, nkeys, df);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(found, df, nkeys, cudaMemcpyDeviceToHost, ctx->stream);

@@ -115,8 +115,6 @@ class Engine:
         if rc:
             self.h = C.c_void_p()
             raise BsgsError(rc, "bsgs_create")
-        if "kernel" not in options and os.environ.get("BSGS_KERNEL"):
-            options["kernel"] = int(os.environ["BSGS_KERNEL"])
         for k, v in options.items():
             self._ck(self.L.bsgs_set_option(self.h, k.encode(), int(v)), f"bsgs_set_option({k})")
         self.cap = 1 << 16
@@ -196,7 +194,7 @@ class Engine:
         self._ck(self.L.bsgs_step_multi(self.h, len(points), _pxy(points), self._hits, self.cap, C.byref(n)), "bsgs_step_multi")
         return self._take(n.value)
 
-    def run(self, P0, D, nwindows, batch=4, stop_after_hits=0):
+    def run(self, P0, D, nwindows, batch=16, stop_after_hits=0):
         n, done = C.c_uint32(), C.c_uint64()
         self._ck(self.L.bsgs_run(self.h, _pxy([P0]), _pxy([D]), nwindows, batch, stop_after_hits, self._hits, self.cap,
                                  C.byref(n), C.byref(done)), "bsgs_run")

@@ -89,7 +89,7 @@ class Search:
         return None
 
 
-def solve(engine, htcpu, T, B, p, w, htsz, pk, pke, target_xy, batch=4, rank=0, world=1, max_windows=None):
+def solve(engine, htcpu, T, B, p, w, htsz, pk, pke, target_xy, batch=16, rank=0, world=1, max_windows=None):
     """Search [pk, pke] for the key of target_xy with `engine` (tables already uploaded).
     Returns (key or None, windows_done, records_seen)."""
     s = Search(T, B, p, w, htsz, pk, target_xy, rank=rank, world=world)

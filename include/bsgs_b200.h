@@ -94,9 +94,9 @@ int  bsgs_ht_device_image(bsgs_ctx *ctx, void **dev_ptr, size_t *bytes);
  * reference overflows into the giant array at record 240, F197:2337 / PTX197:L104-109). */
 int  bsgs_step(bsgs_ctx *ctx, const uint8_t px_le[32], const uint8_t py_le[32],
                bsgs_hit *out, uint32_t cap, uint32_t *nhits);
-/* nwin (1..BSGS_MAX_WINDOWS) consecutive GetJob() windows in ONE launch: pxy_le holds nwin records
- * of 64 bytes (x then y).  Each giant point is loaded once for all windows and one field inversion
- * per thread is shared by all of them.  hits carry the window index. */
+/* nwin (1..BSGS_MAX_WINDOWS) GetJob() windows in ONE launch: pxy_le holds nwin records of 64 bytes
+ * (x then y).  Each giant point is loaded once for all windows and one field inversion per thread
+ * is shared by all of them.  hits carry the window index. */
 #define BSGS_MAX_WINDOWS 16
 int  bsgs_step_multi(bsgs_ctx *ctx, uint32_t nwin, const uint8_t *pxy_le,
                      bsgs_hit *out, uint32_t cap, uint32_t *nhits);
@@ -120,7 +120,9 @@ int  bsgs_probe_keys(bsgs_ctx *ctx, const uint64_t *keys, uint64_t nkeys, uint8_
 /* geometry actually used by the kernel (threads, points per thread, bytes resident) */
 typedef struct { uint32_t grid, block, points_per_thread, sm_count; uint64_t n_giants, bytes_giants, bytes_chain, bytes_table; } bsgs_info;
 int  bsgs_get_info(const bsgs_ctx *ctx, bsgs_info *info);
-/* tuning knobs: "blocks_per_sm", "bucket_bytes" (32|64), "max_windows"; call before uploads */
+/* tuning knobs, call before uploads: "blocks_per_sm" (1..3 resident 256-thread CTAs per SM; the
+ * grid is SMs x this), "max_windows" (sizes the chain buffer), "l2_fetch" (32|64|128: device-wide
+ * DRAM->L2 fetch granularity) */
 int  bsgs_set_option(bsgs_ctx *ctx, const char *name, int64_t value);
 
 /* -- diagnostics ---------------------------------------------------------------------------- */

@@ -1,2 +1,13 @@
-BSGS_KERNEL=3 timeout 600 python -m pytest tests -m gpu -q -x -k "not reference_kernel" 2>&1 | tail -5
-for cfg in "3 1 2 256" "3 4 2 256" "3 8 2 256" "3 8 3 256" "3 16 3 256" "3 8 4 256" "3 8 5 128" "3 8 6 128" "3 16 6 128" "3 8 7 128" "3 8 8 128"; do set -- $cfg; python bench.py --steps 5 --warmup 3 --no-cpu --kernel $1 --nwin $2 --blocks-per-sm $3 --block $4 2>&1 | python -c "import sys,json; j=json.loads(sys.stdin.readlines()[-1]); print('RESULT kernel $1 nwin $2 bps $3 block $4:', round(j['value']/1e9,2), round(j['roofline']['frac'],3))"; done
+BSGS_KERNEL=3 timeout 600 python -m pytest tests -m gpu -q -x -k "not reference_kernel" 2>&1 | tail -3
+run() { python bench.py --steps 5 --warmup 3 --no-cpu --kernel 3 "$@" 2>&1 | python -c "import sys,json; j=json.loads(sys.stdin.readlines()[-1]); print('RESULT $*:', round(j['value']/1e9,2), round(j['roofline']['frac'],3))"; }
+run --variant 5 --nwin 16 --blocks-per-sm 3
+run --variant 5 --nwin 16 --blocks-per-sm 3 --l2-fetch 32
+run --variant 5 --nwin 16 --blocks-per-sm 3 --l2-fetch 128
+run --variant 6 --nwin 16 --blocks-per-sm 3
+run --variant 6 --nwin 16 --blocks-per-sm 3 --l2-fetch 32
+run --variant 7 --nwin 16 --blocks-per-sm 3
+run --variant 8 --nwin 16 --blocks-per-sm 3
+run --variant 6 --nwin 16 --blocks-per-sm 2
+run --variant 7 --nwin 16 --blocks-per-sm 2
+run --variant 8 --nwin 16 --blocks-per-sm 2
+run --variant 8 --nwin 16 --blocks-per-sm 2 --l2-fetch 32
