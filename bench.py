@@ -116,12 +116,13 @@ def run_b200(args):
     t_setup = time.time()
     e.giants_generate()                                              # every rank: 0.1 s of GPU work, no point broadcasting
     bcast = None
+    build_ht = (lambda: e.ht_build_synthetic(seed=args.seed)) if args.synthetic_table else e.ht_generate
     if world == 1:
-        e.ht_build_synthetic(seed=args.seed)
+        build_ht()
     else:                                                            # rank 0 builds, one NCCL broadcast of the htGPU image
         ptr, nbytes = e.ht_staging()
         if rank == 0:
-            e.ht_build_synthetic(seed=args.seed)
+            build_ht()
         buf = torch.as_tensor(DevBuf(ptr, nbytes), device=f"cuda:{local}")
         torch.cuda.synchronize(); dist.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -183,7 +184,8 @@ def run_b200(args):
         line = {
             "metric": "giant-steps/s", "value": value, "unit": "giant-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit Fp)",
-            "data": "synthetic: uniformly random 64-bit table keys (seed %d) in the htGPU layout; real giant array and real puzzle#65 base points" % args.seed,
+            "data": ("synthetic: uniformly random 64-bit table keys (seed %d) in the htGPU layout" % args.seed if args.synthetic_table else
+                     "real baby-step table (w points (j+1)G, generated and sorted on the GPU)") + "; real giant array; real puzzle#65 base points",
             "config": {"workload": wl["name"], "T": T, "B": B, "p": p, "w": w, "htsz": htsz, "windows_per_launch": nwin,
                        "giant_steps_per_launch": steps_per_launch, "keys_per_giant_step": 2 * w, "l2": "inputs (6.6 GB) larger than L2",
                        "grid": info["grid"], "block": info["block"], "points_per_thread": info["points_per_thread"],
@@ -246,7 +248,7 @@ def run_reference(args):
     pts = [s.window_point(j) for j in range(8)]
     # same tables as the product arm (built with the product's table builders, which are parity-tested)
     e = b.Engine(T, B, p, w, htsz, device=0)
-    e.giants_generate(); e.ht_build_synthetic(seed=args.seed)
+    e.giants_generate(); e.ht_generate()
     cpu = cpu_baseline(e, T, B, p, htsz, pts, budget_s=10.0)
     line = {"impl": "reference", "metric": "giant-steps/s", "unit": "giant-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit Fp)",
@@ -283,6 +285,7 @@ def main():
     ap.add_argument("--nwin", type=int, default=16, help="GetJob windows per launch")
     ap.add_argument("--blocks-per-sm", type=int, default=3)
     ap.add_argument("--seed", type=int, default=20261017)
+    ap.add_argument("--synthetic-table", action="store_true", help="uniform random keys instead of the real baby-step table")
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

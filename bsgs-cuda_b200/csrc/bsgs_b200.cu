@@ -46,6 +46,8 @@ struct bsgs_ctx {
     } while (0)
 
 static int alloc_giants(bsgs_ctx* ctx);
+static gs::Tables make_tables(const bsgs_ctx* c);
+static void fill_win(gs::WinConst& wc, const uint8_t* pxy);
 static size_t ht_image_bytes(const bsgs_ctx* c) { return (size_t)c->H * 4 + 4 + (size_t)c->w * 4; }
 
 extern "C" const char* bsgs_strerror(int s) {
@@ -172,27 +174,33 @@ static int alloc_giants(bsgs_ctx* ctx) {
     return BSGS_OK;
 }
 static void to_const(tgen::PtConst& c, const hec::Pt& p) { memcpy(c.x, p.x.v, 32); memcpy(c.y, p.y.v, 32); }
+// slots [0, N) of (gx, gy) <- (k+1)*D, padding slots replicate slot 0
+static int generate_multiples(bsgs_ctx* ctx, uint4* gx, uint4* gy, hec::Pt A) {
+    tgen::PtConst c; to_const(c, A);
+    tgen::k_set_slot<<<1, 32, 0, ctx->stream>>>(gx, gy, ctx->NT, 0, c);
+    for (uint64_t m = 1; m < ctx->N; m *= 2) {
+        uint64_t cnt = m - 1 < ctx->N - m ? m - 1 : ctx->N - m;
+        if (cnt) tgen::k_giants_extend<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(gx, gy, ctx->NT, m, cnt, c);
+        hec::pt_add(A, A, A);                                    // (2m)*D = slot 2m-1
+        to_const(c, A);
+        if (2 * m - 1 < ctx->N) tgen::k_set_slot<<<1, 32, 0, ctx->stream>>>(gx, gy, ctx->NT, 2 * m - 1, c);
+    }
+    uint64_t total = (uint64_t)ctx->NT * ctx->PP;
+    if (total > ctx->N) tgen::k_pad_slots<<<(unsigned)((total - ctx->N + 255) / 256), 256, 0, ctx->stream>>>(gx, gy, ctx->NT, ctx->N, total);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BSGS_OK;
+}
 extern "C" int bsgs_giants_generate(bsgs_ctx* ctx) {
     if (!ctx) return BSGS_E_ARG;
     CU(cudaSetDevice(ctx->dev));
     int rc = alloc_giants(ctx);
     if (rc) return rc;
-    hec::Pt A;                                                   // A = m*D, D = ADDPUBG = -(2w)G  (F197:4689-4698)
+    hec::Pt A;                                                   // D = ADDPUBG = -(2w)G  (F197:4689-4698)
     hec::pt_mul_u64(A, hec::kG, 2 * ctx->w);
     hec::pt_neg(A, A);
-    tgen::PtConst c; to_const(c, A);
-    tgen::k_set_slot<<<1, 32, 0, ctx->stream>>>(ctx->d_gx, ctx->d_gy, ctx->NT, 0, c);
-    for (uint64_t m = 1; m < ctx->N; m *= 2) {
-        uint64_t cnt = m - 1 < ctx->N - m ? m - 1 : ctx->N - m;
-        if (cnt) tgen::k_giants_extend<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_gx, ctx->d_gy, ctx->NT, m, cnt, c);
-        hec::pt_add(A, A, A);                                    // (2m)*D = Q_{2m-1}
-        to_const(c, A);
-        if (2 * m - 1 < ctx->N) tgen::k_set_slot<<<1, 32, 0, ctx->stream>>>(ctx->d_gx, ctx->d_gy, ctx->NT, 2 * m - 1, c);
-    }
-    uint64_t total = (uint64_t)ctx->NT * ctx->PP;
-    if (total > ctx->N) tgen::k_pad_slots<<<(unsigned)((total - ctx->N + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_gx, ctx->d_gy, ctx->NT, ctx->N, total);
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(ctx->stream));
+    rc = generate_multiples(ctx, ctx->d_gx, ctx->d_gy, A);
+    if (rc) return rc;
     ctx->giants_ready = true;
     return BSGS_OK;
 }
@@ -271,6 +279,59 @@ extern "C" int bsgs_ht_build_from_keys(bsgs_ctx* ctx, const uint64_t* keys, uint
     cudaFree(dk);
     return rc;
 }
+// The real baby-step table: key j = low 64 bits of X((j+1)G), j < w (baby(), F197:1162-1235; index base
+// F197:1221), produced by the giant-step kernel in emit mode: a temporary array of (i+1)G, i < N,
+// and centres C_c = c(2N+1) + N + 1, so that centre c yields the multipliers c(2N+1)+1 .. (c+1)(2N+1).
+template <int MINB>
+static cudaError_t launch_emit(const bsgs_ctx* c, const gs::Tables& tb, const gs::WinParams& wp, int nwin) {
+    gs::k_giant_step<256, MINB, 1><<<c->grid, 256, 0, c->stream>>>(tb, wp, nwin);
+    return cudaGetLastError();
+}
+static int generate_baby_keys(bsgs_ctx* ctx, uint64_t* d_keys) {
+    size_t slots = (size_t)ctx->NT * ctx->PP;
+    const uint32_t W = BSGS_MAX_WINDOWS;
+    uint4 *gx = nullptr, *gy = nullptr, *chain = nullptr;
+    auto cleanup = [&]() { cudaFree(gx); cudaFree(gy); cudaFree(chain); };
+    cudaError_t e = cudaMalloc(&gx, slots * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&gy, slots * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&chain, slots * 32 * W);
+    if (e != cudaSuccess) { cleanup(); ctx->last_cuda = (int)e; cudaGetLastError(); return BSGS_E_NOMEM; }
+    int rc = generate_multiples(ctx, gx, gy, hec::kG);
+    if (rc) { cleanup(); return rc; }
+    gs::Tables tb = make_tables(ctx);
+    tb.gx = gx; tb.gy = gy; tb.chain = chain; tb.keys_out = d_keys; tb.nkeys = ctx->w;
+    const uint64_t span = 2 * ctx->N + 1;
+    const uint64_t ncenters = (ctx->w + span - 1) / span;
+    hec::Pt P, S;
+    hec::pt_mul_u64(P, hec::kG, ctx->N + 1);                     // first centre
+    hec::pt_mul_u64(S, hec::kG, span);                           // centre stride
+    for (uint64_t c0 = 0; c0 < ncenters && rc == BSGS_OK; c0 += W) {
+        uint32_t n = (uint32_t)(ncenters - c0 < W ? ncenters - c0 : W);
+        gs::WinParams wp; memset(&wp, 0, sizeof wp);
+        for (uint32_t i = 0; i < n; i++) {
+            uint8_t pxy[64]; hec::store_le(pxy, P.x); hec::store_le(pxy + 32, P.y);
+            fill_win(wp.win[i], pxy);
+            wp.center[i] = (c0 + i) * span + ctx->N + 1;
+            hec::pt_add(P, P, S);
+        }
+        e = ctx->blocks_per_sm >= 3 ? launch_emit<3>(ctx, tb, wp, (int)n) : launch_emit<2>(ctx, tb, wp, (int)n);
+        if (e != cudaSuccess) { ctx->last_cuda = (int)e; cudaGetLastError(); rc = BSGS_E_CUDA; }
+    }
+    e = cudaStreamSynchronize(ctx->stream);
+    if (rc == BSGS_OK && e != cudaSuccess) { ctx->last_cuda = (int)e; cudaGetLastError(); rc = BSGS_E_CUDA; }
+    cleanup();
+    return rc;
+}
+extern "C" int bsgs_ht_generate(bsgs_ctx* ctx) {
+    if (!ctx) return BSGS_E_ARG;
+    CU(cudaSetDevice(ctx->dev));
+    uint64_t* dk = nullptr;
+    CU(cudaMalloc(&dk, (size_t)ctx->w * 8));
+    int rc = generate_baby_keys(ctx, dk);
+    if (rc == BSGS_OK) rc = build_from_device_keys(ctx, dk);
+    cudaFree(dk);
+    return rc;
+}
 extern "C" int bsgs_ht_build_synthetic(bsgs_ctx* ctx, uint64_t seed) {
     if (!ctx) return BSGS_E_ARG;
     CU(cudaSetDevice(ctx->dev));
@@ -321,6 +382,7 @@ static gs::Tables make_tables(const bsgs_ctx* c) {
     tb.csr_off = (const uint32_t*)c->d_ht; tb.csr_tags = tb.csr_off + c->H + 1;
     tb.hit_count = c->d_hits; tb.hits = c->d_hits + 4; tb.hit_cap = c->hit_cap;
     tb.NT = c->NT; tb.PP = c->PP; tb.N = (uint32_t)c->N; tb.mask = (uint32_t)(c->H - 1);
+    tb.keys_out = nullptr; tb.nkeys = 0;
     return tb;
 }
 
@@ -337,7 +399,7 @@ static cudaError_t launch_k(const bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy
     memset(&wp, 0, sizeof wp);
     for (uint32_t i = 0; i < nwin; i++) fill_win(wp.win[i], pxy + 64 * i);
     gs::Tables tb = make_tables(c);
-    gs::k_giant_step<BLOCK, MINB><<<c->grid, BLOCK, 0, c->stream>>>(tb, wp, (int)nwin);
+    gs::k_giant_step<BLOCK, MINB, 0><<<c->grid, BLOCK, 0, c->stream>>>(tb, wp, (int)nwin);
     return cudaGetLastError();
 }
 static cudaError_t launch_any(const bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {

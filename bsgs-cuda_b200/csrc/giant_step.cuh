@@ -40,7 +40,10 @@ struct WinConst {
     uint32_t npx[8];      // p - Px
     uint32_t py2[8];      // 2*Py mod p  (denominator of the tangent, used when Px == Qx)
 };
-struct WinParams { WinConst win[kMaxW]; };     // 2 KB of kernel parameters
+struct WinParams {                             // 2.1 KB of kernel parameters
+    WinConst win[kMaxW];
+    uint64_t center[kMaxW];                    // emit mode only: P_w = center[w] * G
+};
 
 struct Tables {
     const uint4* gx;          // [PP*2][NT] : limbs 0-3 / 4-7 of Qx, slot (r, t) at (2r+h)*NT + t
@@ -54,6 +57,8 @@ struct Tables {
     uint32_t hit_cap;
     uint32_t NT, PP, N;       // threads in the grid, points per thread, giants
     uint32_t mask;            // H - 1
+    uint64_t* keys_out;       // emit mode: keys_out[m - 1] = low 64 bits of X(m*G), m <= nkeys
+    uint64_t nkeys;
 };
 
 struct Fe { uint32_t v[8]; };
@@ -155,11 +160,16 @@ struct FpSector {
 // exact, slow: Px == Qx (true doubling -> code 4), PTX197:L28996-
 __device__ __noinline__ uint64_t double_x_low64_v(Fe px, Fe inv2y) { return double_x_low64(px.v, inv2y.v); }
 
-template <int BLOCK, int MINB>
+// MODE 0: probe every candidate X in the baby-step table and record hits (the giant-step search).
+// MODE 1: the same arithmetic used as a generator: the "giant" array holds (i+1)*G, the windows are
+//         centres C_w*G, and the low 64 bits of X((C_w -+ (i+1))*G) are stored as baby-step keys --
+//         the reference computes these with w sequential batch additions on the CPU
+//         (baby(), 1_9_7File.pb:1162-1235).
+template <int BLOCK, int MINB, int MODE>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_giant_step(const Tables tb, const __grid_constant__ WinParams wp, int W) {
     __shared__ __align__(16) uint32_t s_win[kMaxW * 32];
-    __shared__ uint64_t s_ring[kRing * BLOCK];
+    __shared__ uint64_t s_ring[MODE == 0 ? kRing * BLOCK : 1];
     const uint32_t t = blockIdx.x * BLOCK + threadIdx.x;
     const uint32_t NT = tb.NT;
     const int PP = (int)tb.PP;
@@ -171,8 +181,12 @@ k_giant_step(const Tables tb, const __grid_constant__ WinParams wp, int W) {
     if (t == 0) {
 #pragma unroll 1
         for (int w = 0; w < W; w++) {
-            uint32_t h = s_win[w * 32] & tb.mask, tag = s_win[w * 32 + 1];
-            if (probe_csr(tb.csr_off, tb.csr_tags, h, tag)) record_hit(tb, 5u, 0u, (uint32_t)w);
+            if (MODE == 0) {
+                uint32_t h = s_win[w * 32] & tb.mask, tag = s_win[w * 32 + 1];
+                if (probe_csr(tb.csr_off, tb.csr_tags, h, tag)) record_hit(tb, 5u, 0u, (uint32_t)w);
+            } else if (wp.center[w] <= tb.nkeys) {
+                tb.keys_out[wp.center[w] - 1] = ((uint64_t)s_win[w * 32 + 1] << 32) | s_win[w * 32];
+            }
         }
     }
 
@@ -238,7 +252,13 @@ k_giant_step(const Tables tb, const __grid_constant__ WinParams wp, int W) {
                 fp::fe_add_lazy(sum.v, py.v, s.v);
                 fp::fe_mul(lam.v, sum.v, invd.v);
                 fp::fe_sqr(l2.v, lam.v);
-                ring[(fill + side) * BLOCK] = fp::fe_add_low64_canon(l2.v, u.v);
+                const uint64_t key = fp::fe_add_low64_canon(l2.v, u.v);
+                if (MODE == 0) ring[(fill + side) * BLOCK] = key;
+                else if (live) {                                    // multiplier C - (i+1) (side 0) or C + (i+1) (side 1)
+                    const uint64_t i1 = (uint64_t)r * NT + t + 1, c = wp.center[w];
+                    const uint64_t m = side == 0 ? c - i1 : c + i1;
+                    if (m <= tb.nkeys) tb.keys_out[m - 1] = key;
+                }
                 if (side == 0) {                                    // Py - Qy = Py + (p - Qy); Qy != 0 on this curve
                     const uint32_t z[8] = {FP_P0, FP_P1, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
                     fp::fe_sub_canon(s.v, z, qy.v);
@@ -246,8 +266,10 @@ k_giant_step(const Tables tb, const __grid_constant__ WinParams wp, int W) {
             }
         } else {
             Fe px = lds_fe(sw);
-            ring[fill * BLOCK] = double_x_low64_v(px, invd);        // X(2P)  (code 4)
+            const uint64_t key = double_x_low64_v(px, invd);        // X(2P)  (code 4); cannot occur in emit mode
+            if (MODE == 0) ring[fill * BLOCK] = key;
         }
+        if (MODE == 1) { if (--w < 0) { w = W - 1; r--; } continue; }
         if (fill == 0) ci_first = ci;
         eqmask |= (eq ? 1u : 0u) << (fill >> 1);
         deadmask |= (live ? 0u : 1u) << (fill >> 1);

@@ -30,7 +30,7 @@ class Info(C.Structure):
 
 EXPORTS = ["bsgs_create", "bsgs_destroy", "bsgs_strerror", "bsgs_last_cuda_error", "bsgs_upload_giants", "bsgs_upload_ht",
            "bsgs_giants_staging", "bsgs_giants_commit", "bsgs_ht_staging", "bsgs_ht_commit", "bsgs_step", "bsgs_step_multi",
-           "bsgs_giants_generate", "bsgs_giants_export", "bsgs_ht_build_from_keys", "bsgs_ht_build_synthetic", "bsgs_ht_export", "bsgs_ht_device_image",
+           "bsgs_giants_generate", "bsgs_giants_export", "bsgs_ht_build_from_keys", "bsgs_ht_generate", "bsgs_ht_build_synthetic", "bsgs_ht_export", "bsgs_ht_device_image",
            "bsgs_run", "bsgs_time_launches", "bsgs_probe_bench", "bsgs_probe_keys", "bsgs_get_info", "bsgs_set_option", "bsgs_debug_field"]
 
 _lib = None
@@ -60,6 +60,7 @@ def load():
     L.bsgs_giants_generate.argtypes = [vp]
     L.bsgs_giants_export.argtypes = [vp, vp, C.c_size_t]
     L.bsgs_ht_build_from_keys.argtypes = [vp, vp, u64]
+    L.bsgs_ht_generate.argtypes = [vp]
     L.bsgs_ht_build_synthetic.argtypes = [vp, u64]
     L.bsgs_ht_export.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.bsgs_ht_device_image.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -161,6 +162,10 @@ class Engine:
     def ht_build_from_keys(self, keys: np.ndarray):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         self._ck(self.L.bsgs_ht_build_from_keys(self.h, keys.ctypes.data, len(keys)), "bsgs_ht_build_from_keys")
+
+    def ht_generate(self):
+        """Real baby-step table, generated and sorted on the device."""
+        self._ck(self.L.bsgs_ht_generate(self.h), "bsgs_ht_generate")
 
     def ht_build_synthetic(self, seed=1):
         self._ck(self.L.bsgs_ht_build_synthetic(self.h, seed), "bsgs_ht_build_synthetic")

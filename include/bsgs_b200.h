@@ -80,6 +80,10 @@ int  bsgs_ht_commit(bsgs_ctx *ctx);
  * 64-bit keys, key j being the low 8 bytes of X((j+1)G) (F197:1127, 1221).  The resulting htGPU /
  * htCPU images are byte-identical to the files the reference writes and can be exported. */
 int  bsgs_ht_build_from_keys(bsgs_ctx *ctx, const uint64_t *keys, uint64_t nkeys);
+/* The whole baby-step table on the device: the w keys X((j+1)G) mod 2^64 are produced by the
+ * giant-step kernel itself (replaces GenBabys/baby(), F197:1162-1328: CountCPUs host threads, hours
+ * at w >= 2^30), then sorted into the CSR image as above. */
+int  bsgs_ht_generate(bsgs_ctx *ctx);
 /* measurement only: w uniformly random keys (splitmix64 of seed + j) instead of real baby steps */
 int  bsgs_ht_build_synthetic(bsgs_ctx *ctx, uint64_t seed);
 /* kind 0: htGPU file image (4H + 4 + 4w bytes); kind 1: htCPU file image (4H + 4 + 8w bytes; only

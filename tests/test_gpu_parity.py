@@ -301,3 +301,29 @@ def test_ht_true_baby_keys_device_build(pkg, orc):
     with pkg.Engine(4, 4, 4, w, htsz) as e:
         e.ht_build_from_keys(keys)
         assert bytes(e.ht_export("cpu")) == bytes(cpu)
+
+
+@pytest.mark.parametrize("T,B,p,w,htsz", [(32, 4, 8, 1 << 16, 13), (16, 2, 3, 5000, 9), (64, 20, 100, 100000, 12), (512, 8, 6, 3000, 8),
+                                          (8, 1, 1, 1, 1), (4, 1, 1, 9, 2), (128, 16, 8, 1 << 20, 18)])
+def test_ht_generate_equals_oracle_baby_table(pkg, orc, T, B, p, w, htsz):
+    """Baby-step table generated by the giant-step kernel in emit mode == the reference's table
+    ((j+1)G, low 8 bytes of X, 1_9_7File.pb:1127/1221) as restated by the oracle, byte for byte."""
+    keys = orc.baby_keys(w)
+    cpu, gpu = orc.build_ht(keys, htsz)
+    with pkg.Engine(T, B, p, w, htsz) as e:
+        e.ht_generate()
+        assert bytes(e.ht_export("gpu")) == bytes(gpu)
+        assert bytes(e.ht_export("cpu")) == bytes(cpu)
+
+
+def test_solve_with_device_generated_tables(pkg):
+    """Whole problem with nothing from the oracle: device-generated giants + baby table, key recovered."""
+    T, B, p, w, htsz = 64, 8, 16, 1 << 18, 16
+    pk = 0x8000000000
+    secret = 0xE9AE4933D6                                           # puzzle #40 (BASELINE.json configs[0])
+    target = pkg.ec.parse_pubkey("03a2efa402fd5268400c77c20e574ba86409ededee7c4020e4b9f0edbee53de0d4")
+    with pkg.Engine(T, B, p, w, htsz) as e:
+        e.giants_generate(); e.ht_generate()
+        htcpu = e.ht_export("cpu")
+        key, done, seen = pkg.solve(e, htcpu, T, B, p, w, htsz, pk, 0xffffffffff, target)
+        assert key == secret
