@@ -82,9 +82,15 @@ FP_DEV void mad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
     addc(acc[8], acc[8], 0);
 }
 
-// r = v[0..15] mod p (lazy, < 2^256): fold the high half by (2^32 + 977) twice.
+// r = v[0..15] mod p (lazy, < 2^256): fold the high half by 2^256 = 2^32 + 977 (mod p) twice.
+//
+// First fold: s = lo + hi*977 + (hi << 32), computed as two carry chains of IMAD.WIDE (even limbs of
+// hi onto lo, odd limbs onto hi << 32) and one 9-limb addition.  Its overflow T = s >> 256 satisfies
+// T <= 2^32 + 977 (lo, hi < 2^256), i.e. T = top2*2^32 + top with top2 in {0, 1}.
+// Second fold: r = (s mod 2^256) + T*(2^32 + 977) = ... + top*977 + (top << 32) + top2*(977 << 32) + (top2 << 64);
+// this addend is < 2^67.  If that addition wraps 2^256 once more, the wrapped value is < 2^67, so
+// the final "+ 2^32 + 977" touches limbs 0..2 only.
 FP_DEV void reduce512(uint32_t r[8], uint32_t v[16]) {
-    // t = (hi << 32) + odd products hi[1,3,5,7]*977 at limbs 1..8 (+ carry limb 9)
     uint32_t t[10];
     t[0] = 0;
 #pragma unroll
@@ -95,36 +101,32 @@ FP_DEV void reduce512(uint32_t r[8], uint32_t v[16]) {
     madwc_cc(t[5], t[6], v[13], FP_C0);
     madwc_cc(t[7], t[8], v[15], FP_C0);
     addc(t[9], 0, 0);
-    // lo += even products hi[0,2,4,6]*977 at limbs 0..7 (+ carry limb 8)
     uint32_t l8 = 0;
     madw_cc(v[0], v[1], v[8], FP_C0);
     madwc_cc(v[2], v[3], v[10], FP_C0);
     madwc_cc(v[4], v[5], v[12], FP_C0);
     madwc_cc(v[6], v[7], v[14], FP_C0);
     addc(l8, 0, 0);
-    // s = lo + t  (9 limbs + small top)
-    uint32_t top;
-    add_cc(r[0], v[0], t[0]);
+    uint32_t top, top2;
+    r[0] = v[0];                                   // t[0] == 0
+    add_cc(r[1], v[1], t[1]);
 #pragma unroll
-    for (int i = 1; i < 8; i++) addc_cc(r[i], v[i], t[i]);
+    for (int i = 2; i < 8; i++) addc_cc(r[i], v[i], t[i]);
     addc_cc(top, l8, t[8]);
-    uint32_t top2; addc(top2, t[9], 0);          // top2:top < 2^35, top2 is 0 or tiny
-    // second fold: r += (top2:top) * (2^32 + 977).  top2 can only be non-zero when t[9] carried,
-    // i.e. never for products of 256-bit values (top < 2^34); keep it exact anyway.
-    uint32_t f0 = 0, f1 = 0, f2 = 0;
-    mulw(f0, f1, top, FP_C0);                     // top*977 (64-bit)
-    uint32_t g0, g1; mulw(g0, g1, top2, FP_C0);   // top2*977 at limb 1
-    add_cc(f1, f1, g0); addc(f2, g1, 0);
-    // plus (top2:top) << 32  -> limbs 1,2
-    add_cc(f1, f1, top); addc(f2, f2, top2);
+    addc(top2, t[9], 0);
+    // f = top*977 + (top << 32) as limbs f0..f2, one IMAD.WIDE: (f1:f0) = top*977 + (top << 32 | 0)
+    uint32_t f0 = 0, f1 = top, f2;
+    madw_cc(f0, f1, top, FP_C0);
+    addc(f2, 0, 0);
+    // top2 part: (977 << 32) + (1 << 64), only when top2 == 1 (then top <= 977: no further carries)
+    uint32_t m = 0u - top2;
+    add_cc(f1, f1, m & FP_C0); addc(f2, f2, top2);
     add_cc(r[0], r[0], f0); addc_cc(r[1], r[1], f1); addc_cc(r[2], r[2], f2);
 #pragma unroll
     for (int i = 3; i < 8; i++) addc_cc(r[i], r[i], 0);
     uint32_t k; addc(k, 0, 0);
-    if (k) {                                       // wrapped 2^256 once more (practically never): += 2^32 + 977
-        add_cc(r[0], r[0], FP_C0); addc_cc(r[1], r[1], 1);
-#pragma unroll
-        for (int i = 2; i < 8; i++) addc_cc(r[i], r[i], 0);
+    if (k) {                                       // wrapped once more (probability ~2^-190): r < 2^67 here
+        add_cc(r[0], r[0], FP_C0); addc_cc(r[1], r[1], 1); addc(r[2], r[2], 0);
     }
 }
 

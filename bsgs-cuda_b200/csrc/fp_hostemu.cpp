@@ -8,5 +8,6 @@ void he_inv(uint32_t* r, const uint32_t* a) { fp::fe_inv(r, a); }
 void he_sub_canon(uint32_t* r, const uint32_t* a, const uint32_t* b) { fp::fe_sub_canon(r, a, b); }
 void he_add_lazy(uint32_t* r, const uint32_t* a, const uint32_t* b) { fp::fe_add_lazy(r, a, b); }
 void he_canon(uint32_t* r) { fp::fe_canon(r); }
+void he_reduce512(uint32_t* r, const uint32_t* v16) { uint32_t v[16]; for (int i = 0; i < 16; i++) v[i] = v16[i]; fp::reduce512(r, v); }
 uint64_t he_add_low64_canon(const uint32_t* a, const uint32_t* u) { return fp::fe_add_low64_canon(a, u); }
 }

@@ -78,3 +78,26 @@ def test_low64_of_canonical_sum(he):
     cases += [(a, u % P) for a in EDGE for u in EDGE]
     for a, u in cases:
         assert he.he_add_low64_canon(limbs(a), limbs(u)) == ((a + u) % P) & M64, (hex(a), hex(u))
+
+
+def test_reduce512_all_branches(he):
+    """Arbitrary 512-bit inputs (not only products), including the crafted cases in which the second
+    fold wraps 2^256 again and the one in which the first fold overflows by more than 32 bits."""
+    import ctypes as C
+    C0 = 2**32 + 977
+    rnd = random.Random(9)
+    cases = [rnd.getrandbits(512) for _ in range(2000)] + [2**512 - 1, 0, 2**256 - 1, (2**256 - 1) << 256, P * P, (P - 1) * (2**256 - 1)]
+    for _ in range(300):                                 # second addition wraps: (s mod 2^256) within f of 2^256
+        hi = rnd.getrandbits(256) | (1 << 255)
+        T = (hi * C0) >> 256
+        want_low = 2**256 - 1 - rnd.randrange(0, T * C0 + 1)
+        lo = (want_low - hi * C0) % 2**256
+        cases.append((hi << 256) | lo)
+    for _ in range(100):                                 # top2 = 1
+        hi = 2**256 - 1 - rnd.getrandbits(20)
+        cases.append((hi << 256) | (2**256 - 1 - rnd.getrandbits(40)))
+    for v in cases:
+        arr = (C.c_uint32 * 16)(*[(v >> (32 * i)) & 0xFFFFFFFF for i in range(16)])
+        r = limbs(0)
+        he.he_reduce512(r, arr)
+        assert val(r) % P == v % P, hex(v)
