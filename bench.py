@@ -204,12 +204,25 @@ def run_b200(args):
         }
         if bcast:
             line["ht_broadcast"] = bcast
+        if world == 1 and not args.no_solve and not args.synthetic_table and not args.small:
+            line["solve"] = solve_puzzle65(b, e, s, T, B, p, w, htsz, nwin)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(e, T, B, p, htsz, pts[:8])
     e.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
     return line
+
+
+def solve_puzzle65(b, e, s, T, B, p, w, htsz, nwin):
+    """Whole problem, outside the timed region: recover the puzzle #65 key over [2^64, 2^65) with the
+    resident tables (GetJob windows through bsgs_run, records decoded by the checkerThread mirror)."""
+    t0 = time.time(); htcpu = e.ht_export("cpu"); t_export = time.time() - t0
+    t0 = time.time()
+    key, done, seen = b.solve(e, htcpu, T, B, p, w, htsz, PUZZLE65_PK, PUZZLE65_PKE, s.target, batch=nwin)
+    dt = time.time() - t0
+    return {"key": hex(key) if key else None, "expected": "0x1a838b13505b26867", "ok": key == 0x1a838b13505b26867, "search_s": dt,
+            "windows": done, "records_checked": seen, "htcpu_export_s": t_export}
 
 
 def cpu_baseline(engine, T, B, p, htsz, pts, budget_s=12.0):
@@ -288,6 +301,7 @@ def main():
     ap.add_argument("--synthetic-table", action="store_true", help="uniform random keys instead of the real baby-step table")
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-solve", action="store_true")
     args = ap.parse_args()
     line = run_reference(args) if args.impl == "reference" else run_b200(args)
     if line is not None:

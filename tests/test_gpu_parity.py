@@ -327,3 +327,48 @@ def test_solve_with_device_generated_tables(pkg):
         htcpu = e.ht_export("cpu")
         key, done, seen = pkg.solve(e, htcpu, T, B, p, w, htsz, pk, 0xffffffffff, target)
         assert key == secret
+
+
+# ------------------------------------------------------------------ BASELINE.json full sizes
+@pytest.mark.slow
+def test_full_size_config2_tables_and_puzzle65(pkg, orc):
+    """configs[1] at full size (-t 512 -b 148 -p 256 -w 30 -htsz 28), through size-independent
+    properties: the reference's own run-time validators restated (checkGiantArr 1_9_7File.pb:1524,
+    checkHTpackFile :3101, sortedness :2959) on the device-built tables, a launch compared with the
+    oracle on a slice of the giants, and the published puzzle #65 key recovered."""
+    T, B, p, w, htsz = 512, 148, 256, 1 << 30, 28
+    N, H = T * B * p, 1 << 28
+    rnd = random.Random(65)
+    with pkg.Engine(T, B, p, w, htsz) as e:
+        e.giants_generate(); e.ht_generate()
+        g2 = e.giants_export()
+        assert g2.nbytes == 1241513984
+        D = pyec.neg(pyec.mul(pyec.G, 2 * w))
+        for k in [0, 1, N - 1, N // 2] + [rnd.randrange(N) for _ in range(60)]:      # checkGiantArr: arr[k] == (k+1)*ADDPUBG
+            assert orc.g2_get(g2, T, B, p, k) == pyec.mul(D, k + 1)
+        gpu = e.ht_export("gpu")
+        assert gpu.nbytes == 5368709124
+        off = gpu[:4 * (H + 1)].view(np.uint32)
+        assert off[0] == 0 and off[H] == w and bool(np.all(off[1:] >= off[:-1]))
+        tags = gpu[4 * (H + 1):].view(np.uint32)
+        for h in [rnd.randrange(H) for _ in range(20000)]:                           # ascending tags inside buckets
+            seg = tags[int(off[h]):int(off[h + 1])]
+            assert np.all(seg[1:] >= seg[:-1])
+        js = [0, 1, w - 1] + [rnd.randrange(w) for _ in range(200)]                  # checkHTpackFile: (j+1)G is found
+        keys = np.array([pyec.mul(pyec.G, j + 1)[0] & M64 for j in js], dtype=np.uint64)
+        assert e.probe_keys(keys).all()
+        assert all(orc.probe_htgpu(gpu, htsz, int(k)) for k in keys[:50])
+        assert not e.probe_keys(keys ^ np.uint64(1 << 45)).any()
+        # one launch == the oracle on two slices of the giants (first rows and the ragged tail)
+        target = pkg.ec.parse_pubkey("0230210c23b1a047bc9bdbb13448e67deddc108946de6de639bcc75d47c0216b1b")
+        s = pkg.Search(T, B, p, w, htsz, 1 << 64, target)
+        P0 = s.window_point(3)
+        got = norm_hits(e.step(P0))
+        for lo, hi in ((0, 300000), (N - 200000, N)):
+            exp = [h for h in orc.launch(g2, T, B, p, gpu, htsz, P0, nthreads=16, k_begin=lo, k_end=hi) if h[0] != 5]
+            assert [h for h in got if h[0] != 5 and lo <= h[1] < hi] == exp
+        del gpu, tags, off
+        htcpu = e.ht_export("cpu")
+        assert htcpu.nbytes == 9663676420
+        key, done, seen = pkg.solve(e, htcpu, T, B, p, w, htsz, 1 << 64, (1 << 65) - 1, target)
+        assert key == 0x1a838b13505b26867
