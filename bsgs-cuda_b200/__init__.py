@@ -6,5 +6,6 @@ There is no CPU fallback: importing `native` without the built library raises.""
 from . import ec, formats                                   # noqa: F401
 from .native import Engine, BsgsError, lib_path               # noqa: F401
 from .search import Search, solve                            # noqa: F401
+from . import cli                                            # noqa: F401
 
-__all__ = ["Engine", "BsgsError", "Search", "solve", "ec", "formats", "lib_path"]
+__all__ = ["Engine", "BsgsError", "Search", "solve", "ec", "formats", "cli", "lib_path"]

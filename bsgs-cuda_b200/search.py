@@ -14,6 +14,7 @@ class Search:
         self.pk = pk
         self.target = target_xy
         self.rank, self.world = rank, world
+        self.start_key = start_key
         self.addpubg = ec.neg(ec.mul(ec.G, 2 * w))                     # ADDPUBG  = -(2w)G
         self.centerbig = p * w                                         # CenterBig = p*w
         self.stride = 4 * self.N * w                                   # PRKADDBIG = 4*N*w
@@ -35,10 +36,7 @@ class Search:
     def windows_needed(self, pke):
         """GetJob is called until key_j > pke - pk, tested after the launch (1_9_7File.pb:2512-2518)."""
         width = pke - self.pk
-        total = 0
-        while 1 + total * self.stride <= width:
-            total += 1
-        total = max(total, 1)
+        total = max((width - self.start_key) // self.stride + 1, 1) if width >= self.start_key else 1
         return (total - self.rank + self.world - 1) // self.world if total > self.rank else 0
 
     # ---- checkerThread

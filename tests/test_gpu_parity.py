@@ -372,3 +372,42 @@ def test_full_size_config2_tables_and_puzzle65(pkg, orc):
         assert htcpu.nbytes == 9663676420
         key, done, seen = pkg.solve(e, htcpu, T, B, p, w, htsz, 1 << 64, (1 << 65) - 1, target)
         assert key == 0x1a838b13505b26867
+
+
+# ------------------------------------------------------------------ command line (reference flag surface)
+def test_cli_config0_puzzle40(pkg, tmp_path, monkeypatch):
+    """BASELINE.json configs[0]: puzzle #40, -pk 0x8000000000 -pke 0xffffffffff -w 22 -htsz 25."""
+    import io
+    monkeypatch.chdir(tmp_path)
+    out = io.StringIO()
+    argv = "-t 32 -b 4 -p 16 -w 22 -htsz 25 -pk 0x8000000000 -pke 0xffffffffff -pb 03a2efa402fd5268400c77c20e574ba86409ededee7c4020e4b9f0edbee53de0d4".split()
+    assert pkg.cli.main(argv, out=out) == 0
+    text = out.getvalue()
+    assert "KEY[1]: 0x" + format(0xE9AE4933D6, "064x") in text
+    assert open("win.txt").read().startswith("KEY[1]: 0x" + format(0xE9AE4933D6, "064x"))
+    names = sorted(os.listdir("."))
+    assert pkg.formats.htgpu_name(4194304, 25) in names and pkg.formats.htcpu_name(4194304, 25) in names and "32_4_16_4194304_g2.BIN" in names
+    assert os.path.getsize(pkg.formats.htcpu_name(4194304, 25)) == 167772164 and os.path.getsize(pkg.formats.htgpu_name(4194304, 25)) == 150994948
+    # second run: tables are loaded from the files the first run wrote (reference behaviour, Save_HTpacked 1_9_7File.pb:3645-3759)
+    out2 = io.StringIO()
+    assert pkg.cli.main(argv, out=out2) == 0 and "Load hashtable" in out2.getvalue() and "KEY[1]" in out2.getvalue()
+
+
+def test_cli_infile_sequential_targets(pkg, tmp_path, monkeypatch):
+    """configs[3] in miniature: -infile with several pubkeys over one range, tables loaded once."""
+    import io
+    monkeypatch.chdir(tmp_path)
+    rnd = random.Random(20261017)
+    pk = 0x49dccfd96dc5df56487436f5a1b18c4f5d34f65ddb48cb5e0000000000000000 >> 200 << 36      # a 2^36-wide range
+    secrets = [pk + rnd.randrange(1, 1 << 36) for _ in range(4)]
+    with open("pubs.txt", "w") as f:
+        for i, s in enumerate(secrets):
+            pt = pyec.mul(pyec.G, s)
+            f.write((pkg.ec.compress(pt) if i % 2 else format(pt[0], "064x") + format(pt[1], "064x")) + "\n")
+    out = io.StringIO()
+    argv = f"-t 32 -b 4 -p 16 -w 18 -htsz 16 -pk {pk:x} -pke {pk + (1 << 36):x} -infile pubs.txt".split()
+    assert pkg.cli.main(argv, out=out) == 0
+    text = out.getvalue()
+    for i, s in enumerate(secrets, start=1):
+        assert f"KEY[{i}]: 0x{s:064x}" in text
+    assert text.count("Generate") == 2 and "found 4 of 4" in text                  # tables built once (baby + giants)
