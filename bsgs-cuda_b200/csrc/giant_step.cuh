@@ -85,7 +85,7 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 __device__ __noinline__ bool probe_csr(const uint32_t* off, const uint32_t* tags, uint32_t h, uint32_t tag) {
     uint32_t lo = off[h], hi = off[h + 1];
     while (lo < hi) {
-        uint32_t c = (lo + hi) >> 1, t = tags[c];
+        uint32_t c = lo + ((hi - lo) >> 1), t = tags[c];      // offsets exceed 2^31 at w > 2^31: no lo + hi
         if (tag > t) lo = c + 1; else if (tag < t) hi = c; else return true;
     }
     return false;

@@ -411,3 +411,22 @@ def test_cli_infile_sequential_targets(pkg, tmp_path, monkeypatch):
     for i, s in enumerate(secrets, start=1):
         assert f"KEY[{i}]: 0x{s:064x}" in text
     assert text.count("Generate") == 2 and "found 4 of 4" in text                  # tables built once (baby + giants)
+
+
+@pytest.mark.slow
+def test_full_size_config5_max_table(pkg):
+    """configs[4] (-w 31.5 -htsz 29): 3,037,000,499 entries, CSR offsets beyond 2^31.  Members are found
+    (incl. the last entries, whose offsets are the largest), non-members are not, image size as SURVEY 8a."""
+    w, htsz = pkg.ec.parse_w("31.5"), 29
+    assert w == 3037000499
+    rnd = random.Random(5)
+    with pkg.Engine(512, 148, 256, w, htsz) as e:
+        e.ht_generate()
+        ptr, nbytes = e.ht_device_image()
+        assert nbytes == 14295485648
+        js = [0, 1, w - 1, w - 2, (1 << 31) - 1, 1 << 31, (1 << 31) + 1] + [rnd.randrange(w) for _ in range(120)]
+        keys = np.array([pyec.mul(pyec.G, j + 1)[0] & M64 for j in js], dtype=np.uint64)
+        assert e.probe_keys(keys).all()
+        assert not e.probe_keys(keys ^ np.uint64(1 << 50)).any()
+        ms, found = e.probe_bench(1 << 26, seed=7, iters=1)
+        assert found <= 64                                          # expected 2^26 * 5.66 * 2^-61 * ... ~ 0.2
