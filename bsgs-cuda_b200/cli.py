@@ -40,7 +40,7 @@ def cut_hex(s: str) -> str:                                          # cutHex, 1
 
 def parse_args(argv):
     o = dict(DEFAULTS)
-    o.update(infile=None, wl=None, sf=1, pb_given=False, pk_str="01", pke_str="1ffffffffffffffff")
+    o.update(infile=None, wl=None, sf=1, pb_given=False, pk_str="01", pke_str="1ffffffffffffffff", nosave=False)
     i = 0
     takes = {"-t": ("t", int), "-b": ("b", int), "-p": ("p", int), "-d": ("d", str), "-htsz": ("htsz", int), "-infile": ("infile", str),
              "-wl": ("wl", str), "-sf": ("sf", int)}
@@ -49,6 +49,8 @@ def parse_args(argv):
         val = argv[i + 1] if i + 1 < len(argv) and not (argv[i + 1].startswith("-") and len(argv[i + 1]) > 1 and not argv[i + 1][1].isdigit()) else None
         if a == "-h":
             raise UsageError(__doc__)
+        if a == "-nosave":                                           # extension: keep the generated tables in HBM/RAM only
+            o["nosave"] = True; i += 1; continue
         if a in takes:
             if val is not None:
                 o[takes[a][0]] = takes[a][1](val); i += 1
@@ -117,8 +119,10 @@ def load_or_build_tables(o, engines, log):
     else:
         log(f"Generate {w} baby points on GPU#{o['devices'][0]}")
         e0.ht_generate()
-        htcpu = e0.ht_export("cpu"); htgpu = e0.ht_export("gpu")
-        formats.save(f_cpu, htcpu); formats.save(f_gpu, htgpu)
+        htcpu = e0.ht_export("cpu")
+        htgpu = e0.ht_export("gpu") if (len(engines) > 1 or not o["nosave"]) else None
+        if not o["nosave"]:
+            formats.save(f_cpu, htcpu); formats.save(f_gpu, htgpu)
         for e in engines[1:]:
             e.upload_ht(htgpu)
     if have(f_g2, formats.g2_bytes(T, B, p)):
@@ -130,7 +134,8 @@ def load_or_build_tables(o, engines, log):
         log(f"Generate {T * B * p} giant points on GPU")
         for e in engines:
             e.giants_generate()
-        formats.save(f_g2, e0.giants_export())
+        if not o["nosave"]:
+            formats.save(f_g2, e0.giants_export())
     log(f"Tables ready in {time.time() - t0:.1f}s")
     return htcpu
 

@@ -228,6 +228,13 @@ FP_DEV void fe_canon(uint32_t r[8]) {
 }
 
 FP_DEV bool fe_is_zero(const uint32_t a[8]) { return (a[0] | a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7]) == 0; }
+// same predicate, arranged so that the common case costs one compare and a never-taken branch
+FP_DEV bool fe_is_zero_rare(const uint32_t a[8]) {
+#if defined(__CUDA_ARCH__)
+    if (__builtin_expect(a[0] != 0u, 1)) return false;
+#endif
+    return fe_is_zero(a);
+}
 FP_DEV bool fe_eq(const uint32_t a[8], const uint32_t b[8]) {
     return ((a[0] ^ b[0]) | (a[1] ^ b[1]) | (a[2] ^ b[2]) | (a[3] ^ b[3]) | (a[4] ^ b[4]) | (a[5] ^ b[5]) | (a[6] ^ b[6]) | (a[7] ^ b[7])) == 0;
 }

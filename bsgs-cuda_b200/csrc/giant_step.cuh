@@ -202,7 +202,7 @@ k_giant_step(const Tables tb, const __grid_constant__ WinParams wp, int W) {
             Fe qx = ldg_fe(tb.gx + (size_t)(2 * r) * NT + t, tb.gx + (size_t)(2 * r + 1) * NT + t);
             Fe d;
             { Fe px = lds_fe(s_win + w * 32); fp::fe_sub_canon(d.v, px.v, qx.v); }
-            if (__builtin_expect(fp::fe_is_zero(d.v), 0)) d = lds_fe(s_win + w * 32 + 24);          // 2*Py
+            if (fp::fe_is_zero_rare(d.v)) d = lds_fe(s_win + w * 32 + 24);          // 2*Py
             Fe n; fp::fe_mul(n.v, acc.v, d.v); acc = n;
             size_t co = (size_t)ci * 2 * NT + t;
             st8_stream(tb.chain + co, tb.chain + co + NT, acc.v);
@@ -238,7 +238,7 @@ k_giant_step(const Tables tb, const __grid_constant__ WinParams wp, int W) {
         }
         Fe d;
         { Fe px = lds_fe(sw); fp::fe_sub_canon(d.v, px.v, qx.v); }
-        const bool eq = __builtin_expect(fp::fe_is_zero(d.v), 0);
+        const bool eq = fp::fe_is_zero_rare(d.v);
         if (eq) d = lds_fe(sw + 24);
         Fe invd;
         fp::fe_mul(invd.v, inv.v, cprev.v);                        // 1 / d_ci

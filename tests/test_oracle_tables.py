@@ -173,3 +173,30 @@ def test_planted_codes_4_and_5(orc):
             hits4 += 1
             assert st.check_hit(cpu2, 4, k, wkey, P0) == secret
     assert hits4 > 0
+
+
+@pytest.mark.slow
+def test_config1_plumbing_puzzle40_on_cpu(orc):
+    """BASELINE.json configs[0] at its full table size, CPU only: -pk 0x8000000000 -pke 0xffffffffff -w 22 -htsz 25,
+    tables built with the Curve64 restatement, windows enumerated by GetJob, records decoded by the
+    checkerThread restatement -> key 0xE9AE4933D6 (-t 32 -b 4 -p 16, 16 windows)."""
+    T, B, p, w, htsz = 32, 4, 16, 1 << 22, 25
+    pk, pke, secret = 0x8000000000, 0xffffffffff, 0xE9AE4933D6
+    keys = orc.baby_keys(w)
+    cpu, gpu = orc.build_ht(keys, htsz)
+    assert cpu.nbytes == 167772164 and gpu.nbytes == 150994948
+    g2 = orc.build_g2(T, B, p, w)
+    target = orc.parse_pubkey("03a2efa402fd5268400c77c20e574ba86409ededee7c4020e4b9f0edbee53de0d4")
+    assert target == pyec.mul(pyec.G, secret)
+    s = orc.SearchState(T, B, p, w, htsz, pk, target)
+    found, windows = None, 0
+    while found is None and windows < 20:
+        wkey, P = s.get_job()
+        windows += 1
+        for code, idx in orc.launch(g2, T, B, p, gpu, htsz, P):
+            k = s.check_hit(cpu, code, idx, wkey, P)
+            if k is not None:
+                found = k
+        if wkey > pke - pk:
+            break
+    assert found == secret and windows <= 17
