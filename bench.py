@@ -112,6 +112,8 @@ def run_b200(args):
     N = T * B * p
     nwin = args.nwin
     opts = dict(max_windows=max(nwin, 1), blocks_per_sm=args.blocks_per_sm)
+    if args.l2_fetch:
+        opts["l2_fetch"] = args.l2_fetch
     e = b.Engine(T, B, p, w, htsz, device=local, **opts)
     t_setup = time.time()
     e.giants_generate()                                              # every rank: 0.1 s of GPU work, no point broadcasting
@@ -181,6 +183,12 @@ def run_b200(args):
         load = w / (1 << htsz)
         bytes_per_step = 8 + 4 * load + 32                           # probe (offset pair + tags) + giant stream
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tf) and not args.small:
+            tj = json.load(open(tf))
+            if tj.get("windows_per_launch") == nwin:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         line = {
             "metric": "giant-steps/s", "value": value, "unit": "giant-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit Fp)",
@@ -195,7 +203,7 @@ def run_b200(args):
                     "api": "bsgs_run (C ABI, host buffers)", "ms_per_step": te / K},
             "gpu_launches": K,
             "roofline": {"bound": "imad", "achieved": ach_m32 / 1e12, "peak": peak_m32 / 1e12, "unit": "T mad32/s", "frac": ach_m32 / peak_m32,
-                         "traffic": None, "per_unit": f"{M32_PER_STEP} mad32 per giant step", "peak_source": ip_how,
+                         "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r1_traffic.json)", "per_unit": f"{M32_PER_STEP} mad32 per giant step", "peak_source": ip_how,
                          "imad_lanes_per_clk_per_sm": lanes, "sm_mhz_for_peak": sm_max},
             "roofline_hbm": {"bound": "hbm", "achieved": value / world * bytes_per_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": value / world * bytes_per_step / 1e9 / hbm_peak, "per_unit": f"{bytes_per_step:.1f} B per giant step",
@@ -297,6 +305,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nwin", type=int, default=16, help="GetJob windows per launch")
     ap.add_argument("--blocks-per-sm", type=int, default=3)
+    ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (32|64|128), 0 = leave")
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--synthetic-table", action="store_true", help="uniform random keys instead of the real baby-step table")
     ap.add_argument("--small", action="store_true")

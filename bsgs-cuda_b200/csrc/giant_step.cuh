@@ -141,8 +141,12 @@ struct FpSector {
     uint4 a, b;
     __device__ __forceinline__ void load(const Tables& tb, uint32_t h) {
         const uint4* p = reinterpret_cast<const uint4*>(tb.buckets) + 2ull * h;
-        // one random 32-byte sector, never reused: keep it out of L1 and first in line for L2 eviction
-        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        // One random 32-byte sector, never reused: a single 256-bit load (LDG.E.256) kept out of L1,
+        // first in line for L2 eviction, and with the smallest L2 fill size (64 B).  Measured with ncu on
+        // config 2: the default fill promotes every miss to the whole 128-byte line (90.7 GB of DRAM reads
+        // per 16-window launch), the 64 B hint reads 51.4 GB at the same speed; two 128-bit loads instead
+        // of one 256-bit load run 1.5x slower.
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
     }
     // true when the exact lookup is required: some halfword equals the fingerprint (this includes

@@ -9,7 +9,8 @@ MAX_WINDOWS = 16
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libbsgs_b200.so")
+    """The in-tree CUDA library (BSGS_B200_LIB overrides the path: used to A/B experimental builds)."""
+    return os.environ.get("BSGS_B200_LIB") or os.path.join(_HERE, "libbsgs_b200.so")
 
 
 class BsgsError(RuntimeError):
