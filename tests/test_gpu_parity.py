@@ -430,3 +430,68 @@ def test_full_size_config5_max_table(pkg):
         assert not e.probe_keys(keys ^ np.uint64(1 << 50)).any()
         ms, found = e.probe_bench(1 << 26, seed=7, iters=1)
         assert found <= 64                                          # expected 2^26 * 5.66 * 2^-61 * ... ~ 0.2
+
+
+# ------------------------------------------------------------------ boundary behaviour
+def test_record_cap_overflow_is_reported_not_overrun(pkg, orc):
+    """More hits than `cap`: status BSGS_E_OVERFLOW, true count returned, first `cap` records stored
+    (the reference overruns into the giant array at record 240, 1_9_7File.pb:2337)."""
+    import ctypes as C
+    T, B, p, w, htsz = 32, 4, 8, 4000, 4
+    N = T * B * p
+    rnd = random.Random(3)
+    Ppt = random_point(rnd)
+    xs = [candidate_x(Ppt, w, k, 1 + (k & 1)) for k in range(0, 40)]
+    cpu, gpu = orc.build_ht(synthetic_keys(w, xs, 9), htsz)
+    g2 = orc.build_g2(T, B, p, w)
+    exp = orc.launch(g2, T, B, p, gpu, htsz, Ppt)
+    assert len(exp) >= 40
+    with pkg.Engine(T, B, p, w, htsz) as e:
+        e.upload_giants(g2); e.upload_ht(gpu)
+        hits = (pkg.native.Hit * 8)(); n = C.c_uint32()
+        rc = e.L.bsgs_step(e.h, Ppt[0].to_bytes(32, "little"), Ppt[1].to_bytes(32, "little"), hits, 8, C.byref(n))
+        assert rc == -6 and n.value == len(exp)
+        assert all((hits[i].code, hits[i].idx) in set(exp) for i in range(8))
+        assert norm_hits(e.step(Ppt)) == norm_hits(exp)            # the context stays usable
+
+
+def test_two_contexts_driven_from_two_threads(pkg, orc):
+    """One context per host thread, like CreateThread(@cuda(), i) (1_9_7File.pb:4776)."""
+    import threading
+    T, B, p, w, htsz = 32, 4, 8, 3000, 9
+    g2 = orc.build_g2(T, B, p, w)
+    rnd = random.Random(12)
+    pts = [random_point(rnd) for _ in range(6)]
+    xs = [candidate_x(pt, w, (i * 91) % (T * B * p), 1 + (i & 1)) for i, pt in enumerate(pts)]
+    cpu, gpu = orc.build_ht(synthetic_keys(w, xs, 4), htsz)
+    exp = [norm_hits(orc.launch(g2, T, B, p, gpu, htsz, pt)) for pt in pts]
+    res = {}
+
+    def work(tid):
+        with pkg.Engine(T, B, p, w, htsz) as e:
+            e.upload_giants(g2); e.upload_ht(gpu)
+            res[tid] = [norm_hits(e.step(pt)) for pt in pts for _ in range(3)][::3]
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert res[0] == exp and res[1] == exp
+
+
+def test_reupload_and_argument_errors(pkg, orc):
+    T, B, p, w, htsz = 16, 2, 4, 1000, 7
+    g2 = orc.build_g2(T, B, p, w)
+    rnd = random.Random(1)
+    Ppt = random_point(rnd)
+    k1, k2 = synthetic_keys(w, [candidate_x(Ppt, w, 3, 1)], 1), synthetic_keys(w, [candidate_x(Ppt, w, 5, 2)], 2)
+    _, gpu1 = orc.build_ht(k1, htsz); _, gpu2 = orc.build_ht(k2, htsz)
+    with pkg.Engine(T, B, p, w, htsz) as e:
+        e.upload_giants(g2)
+        e.upload_ht(gpu1); a = norm_hits(e.step(Ppt))
+        e.upload_ht(gpu2); b2 = norm_hits(e.step(Ppt))             # table replaced in place
+        assert (1, 3) in a and (2, 5) in b2 and a == norm_hits(orc.launch(g2, T, B, p, gpu1, htsz, Ppt)) and b2 == norm_hits(orc.launch(g2, T, B, p, gpu2, htsz, Ppt))
+        with pytest.raises(pkg.BsgsError):
+            e.step_multi([Ppt] * 17)                               # more than BSGS_MAX_WINDOWS
+        with pytest.raises(pkg.BsgsError):
+            e.ht_export("cpu")                                     # payloads unknown after a plain htGPU upload
+        with pytest.raises(pkg.BsgsError):
+            e.upload_giants(g2[:-64])
