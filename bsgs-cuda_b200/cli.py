@@ -113,9 +113,9 @@ def load_or_build_tables(o, engines, log):
     have = lambda f, n: os.path.exists(f) and os.path.getsize(f) == n                       # noqa: E731
     if have(f_cpu, formats.htcpu_bytes(w, htsz)) and have(f_gpu, formats.htgpu_bytes(w, htsz)):
         log(f"Load hashtable from {f_gpu}")
-        htgpu = formats.load(f_gpu); htcpu = formats.load(f_cpu)
+        htcpu = formats.load(f_cpu)
         for e in engines:
-            e.upload_ht(htgpu)
+            e.upload_htcpu(htcpu)                                # tags + payloads: enables device-side verification
     else:
         log(f"Generate {w} baby points on GPU#{o['devices'][0]}")
         e0.ht_generate()
@@ -124,7 +124,9 @@ def load_or_build_tables(o, engines, log):
         if not o["nosave"]:
             formats.save(f_cpu, htcpu); formats.save(f_gpu, htgpu)
         for e in engines[1:]:
-            e.upload_ht(htgpu)
+            e.upload_htcpu(htcpu)
+    for e in engines:
+        e.set_verify(True)
     if have(f_g2, formats.g2_bytes(T, B, p)):
         log(f"Load giants from {f_g2}")
         g2 = formats.load(f_g2)
@@ -198,8 +200,8 @@ def main(argv=None, out=sys.stdout) -> int:
                 while done < nwin and not state["stop"]:
                     chunk = min(nwin - done, 16)
                     hits, d = e.run(s.window_point(done), s.D, chunk, batch=chunk, stop_after_hits=1)
-                    for code, idx, win in hits:
-                        k = s.check_hit(htcpu, code, idx, done + win)
+                    for (code, idx, win), payload in zip(hits, list(e.payloads)):
+                        k = s.check_verified(code, idx, done + win, payload) if payload != 0xFFFFFFFF else s.check_hit(htcpu, code, idx, done + win)
                         if k is not None:
                             with state["lock"]:
                                 state["key"], state["stop"] = k, True

@@ -4,6 +4,7 @@
 #include "giant_step.cuh"
 #include "table_build.cuh"
 #include "table_gen.cuh"
+#include "verify.cuh"
 #include "host_ec.h"
 #include <cuda_runtime.h>
 #include <new>
@@ -26,6 +27,10 @@ struct bsgs_ctx {
     uint32_t* d_js = nullptr;        // payload j of every CSR item (htCPU image = tags interleaved with these)
     uint32_t* d_hits = nullptr;      // [0] counter, [4..] records (3 u32 each)
     unsigned long long* d_scratch = nullptr;
+    uint32_t* d_verdict = nullptr;   // per record: payload j / accepted / rejected (device-side verification)
+    uint32_t* h_verdict = nullptr;
+    bool verify = false;
+    gs::WinParams last_wp;           // window constants of the launch whose records are being collected
     uint32_t hit_cap = 1u << 16;
     uint32_t* h_hits = nullptr;      // pinned mirror
     size_t chain_bytes = 0, giants_bytes = 0, table_bytes = 0;
@@ -88,6 +93,8 @@ extern "C" int bsgs_create(bsgs_ctx** out, int device, uint32_t T, uint32_t B, u
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->e1);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_hits, 16 + (size_t)ctx->hit_cap * 12);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_scratch, 64);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_verdict, (size_t)ctx->hit_cap * 4);
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_verdict, (size_t)ctx->hit_cap * 4);
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_hits, 16 + (size_t)ctx->hit_cap * 12);
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_hits, 0, 16, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -102,7 +109,8 @@ extern "C" void bsgs_destroy(bsgs_ctx* ctx) {
     cudaSetDevice(ctx->dev);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_g2_stage); cudaFree(ctx->d_gx); cudaFree(ctx->d_gy); cudaFree(ctx->d_chain);
-    cudaFree(ctx->d_ht); cudaFree(ctx->d_buckets); cudaFree(ctx->d_js); cudaFree(ctx->d_hits); cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_ht); cudaFree(ctx->d_buckets); cudaFree(ctx->d_js); cudaFree(ctx->d_hits); cudaFree(ctx->d_scratch); cudaFree(ctx->d_verdict);
+    if (ctx->h_verdict) cudaFreeHost(ctx->h_verdict);
     if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
     if (ctx->e0) cudaEventDestroy(ctx->e0);
     if (ctx->e1) cudaEventDestroy(ctx->e1);
@@ -113,6 +121,7 @@ extern "C" void bsgs_destroy(bsgs_ctx* ctx) {
 
 extern "C" int bsgs_set_option(bsgs_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return BSGS_E_ARG;
+    if (!strcmp(name, "verify")) { ctx->verify = value != 0; return BSGS_OK; }      // may be toggled at any time
     if (ctx->d_gx || ctx->d_buckets) return BSGS_E_STATE;       // geometry is baked into the layouts
     if (!strcmp(name, "blocks_per_sm")) { if (value < 1 || value > 3) return BSGS_E_ARG; ctx->blocks_per_sm = (uint32_t)value; compute_geometry(ctx); return BSGS_OK; }
     if (!strcmp(name, "max_windows")) { if (value < 1 || value > BSGS_MAX_WINDOWS) return BSGS_E_ARG; ctx->max_windows = (uint32_t)value; return BSGS_OK; }
@@ -250,6 +259,28 @@ extern "C" int bsgs_upload_ht(bsgs_ctx* ctx, const void* htgpu, size_t bytes) {
     CU(cudaMemcpyAsync(d, htgpu, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_js) { cudaFree(ctx->d_js); ctx->d_js = nullptr; }   // payloads of a previous device build are stale
+    return bsgs_ht_commit(ctx);
+}
+
+// htCPU file image (4H + 4 + 8w bytes): the same table with the payloads j, which device-side
+// verification needs.  Replaces bsgs_upload_ht for hosts that loaded <...>_htCPUv0.BIN.
+extern "C" int bsgs_upload_htcpu(bsgs_ctx* ctx, const void* htcpu, size_t bytes) {
+    size_t head = ((size_t)(ctx ? ctx->H : 0) + 1) * 4;
+    if (!ctx || !htcpu || bytes != head + (size_t)ctx->w * 8) return BSGS_E_ARG;
+    void* d; size_t n; int rc = bsgs_ht_staging(ctx, &d, &n);
+    if (rc) return rc;
+    if (!ctx->d_js) CU(cudaMalloc(&ctx->d_js, (size_t)ctx->w * 4 + 16));
+    uint2* items = nullptr;
+    CU(cudaMalloc(&items, (size_t)ctx->w * 8 + 16));
+    cudaError_t e = cudaMemcpyAsync(d, htcpu, head, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(items, (const uint8_t*)htcpu + head, (size_t)ctx->w * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && ctx->w) {
+        vfy::k_split_items<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(items, (uint32_t*)d + ctx->H + 1, ctx->d_js, ctx->w);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(items);
+    CU(e);
     return bsgs_ht_commit(ctx);
 }
 
@@ -394,15 +425,15 @@ static void fill_win(gs::WinConst& wc, const uint8_t* pxy) {
 }
 
 template <int BLOCK, int MINB>
-static cudaError_t launch_k(const bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
-    gs::WinParams wp;
+static cudaError_t launch_k(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
+    gs::WinParams& wp = c->last_wp;
     memset(&wp, 0, sizeof wp);
     for (uint32_t i = 0; i < nwin; i++) fill_win(wp.win[i], pxy + 64 * i);
     gs::Tables tb = make_tables(c);
     gs::k_giant_step<BLOCK, MINB, 0><<<c->grid, BLOCK, 0, c->stream>>>(tb, wp, (int)nwin);
     return cudaGetLastError();
 }
-static cudaError_t launch_any(const bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
+static cudaError_t launch_any(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
     if (nwin < 1 || nwin > BSGS_MAX_WINDOWS) return cudaErrorInvalidValue;
     switch (c->blocks_per_sm) {
         case 1: case 2: return launch_k<256, 2>(c, nwin, pxy);
@@ -422,14 +453,26 @@ static int collect_hits(bsgs_ctx* ctx, uint32_t window_base, bsgs_hit* out, uint
     if (stored > eager) {
         CU(cudaMemcpyAsync(ctx->h_hits + 4 + eager * 3, ctx->d_hits + 4 + eager * 3, (size_t)(stored - eager) * 12, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    const bool verify = ctx->verify && ctx->d_js;
+    if (verify) {                                                // re-examine every record where it was produced
+        gs::Tables tb = make_tables(ctx);
+        vfy::k_verify_hits<<<(stored + 31) / 32, 32, 0, ctx->stream>>>(tb, ctx->last_wp, ctx->d_js, stored, ctx->d_verdict);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(ctx->h_verdict, ctx->d_verdict, (size_t)stored * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CU(cudaMemsetAsync(ctx->d_hits, 0, 4, ctx->stream));         // F197:2500-2504
     CU(cudaStreamSynchronize(ctx->stream));
     int rc = cnt > ctx->hit_cap ? BSGS_E_OVERFLOW : BSGS_OK;
     for (uint32_t i = 0; i < stored; i++) {
+        uint32_t payload = 0xFFFFFFFFu;
+        if (verify) {
+            payload = ctx->h_verdict[i];
+            if (payload == 0xFFFFFFFFu) continue;                // false positive of the 32-bit-tag table: dropped
+        }
         uint32_t pos = *nhits;
         if (pos < cap && out) {
             out[pos].code = ctx->h_hits[4 + 3 * i]; out[pos].idx = ctx->h_hits[4 + 3 * i + 1];
-            out[pos].window = window_base + ctx->h_hits[4 + 3 * i + 2]; out[pos].reserved = 0;
+            out[pos].window = window_base + ctx->h_hits[4 + 3 * i + 2]; out[pos].reserved = payload;
         } else rc = BSGS_E_OVERFLOW;
         (*nhits)++;
     }

@@ -215,7 +215,7 @@ k_giant_step(const Tables tb, const __grid_constant__ WinParams wp, int W) {
     }
 
     // ---------------- one inversion per thread ----------------
-    Fe inv; fp::fe_inv(inv.v, acc.v);
+    Fe inv; fp::fe_inv(inv.v, acc.v);                                // (a by-value wrapper keeps inv out of local memory but costs 3 spills at 80 registers: measured slower)
 
     // ---------------- PASS 2: unwind, slopes, X, keys -> ring -> probe bursts ----------------
     int fill = 0, ci_first = 0; uint32_t eqmask = 0, deadmask = 0;

@@ -29,7 +29,7 @@ class Info(C.Structure):
                 ("n_giants", C.c_uint64), ("bytes_giants", C.c_uint64), ("bytes_chain", C.c_uint64), ("bytes_table", C.c_uint64)]
 
 
-EXPORTS = ["bsgs_create", "bsgs_destroy", "bsgs_strerror", "bsgs_last_cuda_error", "bsgs_upload_giants", "bsgs_upload_ht",
+EXPORTS = ["bsgs_create", "bsgs_destroy", "bsgs_strerror", "bsgs_last_cuda_error", "bsgs_upload_giants", "bsgs_upload_ht", "bsgs_upload_htcpu",
            "bsgs_giants_staging", "bsgs_giants_commit", "bsgs_ht_staging", "bsgs_ht_commit", "bsgs_step", "bsgs_step_multi",
            "bsgs_giants_generate", "bsgs_giants_export", "bsgs_ht_build_from_keys", "bsgs_ht_generate", "bsgs_ht_build_synthetic", "bsgs_ht_export", "bsgs_ht_device_image",
            "bsgs_run", "bsgs_time_launches", "bsgs_probe_bench", "bsgs_probe_keys", "bsgs_get_info", "bsgs_set_option", "bsgs_debug_field"]
@@ -54,6 +54,7 @@ def load():
     L.bsgs_last_cuda_error.argtypes = [vp]
     L.bsgs_upload_giants.argtypes = [vp, vp, C.c_size_t]
     L.bsgs_upload_ht.argtypes = [vp, vp, C.c_size_t]
+    L.bsgs_upload_htcpu.argtypes = [vp, vp, C.c_size_t]
     L.bsgs_giants_staging.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.bsgs_giants_commit.argtypes = [vp]
     L.bsgs_ht_staging.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -121,6 +122,8 @@ class Engine:
             self._ck(self.L.bsgs_set_option(self.h, k.encode(), int(v)), f"bsgs_set_option({k})")
         self.cap = 1 << 16
         self._hits = (Hit * self.cap)()
+        self.verify = bool(options.get("verify", 0))
+        self.payloads = []                                   # parallel to the last returned records (verify=1): j or 0xFFFFFFFE
 
     def _ck(self, rc, what, allow=()):
         if rc and rc not in allow:
@@ -135,6 +138,16 @@ class Engine:
     def upload_ht(self, htgpu: np.ndarray):
         htgpu = np.ascontiguousarray(htgpu)
         self._ck(self.L.bsgs_upload_ht(self.h, htgpu.ctypes.data, htgpu.nbytes), "bsgs_upload_ht")
+
+    def upload_htcpu(self, htcpu: np.ndarray):
+        """The htCPU file image: same table plus the payloads j (needed by verify=1)."""
+        htcpu = np.ascontiguousarray(htcpu)
+        self._ck(self.L.bsgs_upload_htcpu(self.h, htcpu.ctypes.data, htcpu.nbytes), "bsgs_upload_htcpu")
+
+    def set_verify(self, on: bool):
+        """Device-side verification of hit records: false positives dropped, payload j attached."""
+        self._ck(self.L.bsgs_set_option(self.h, b"verify", 1 if on else 0), "bsgs_set_option(verify)")
+        self.verify = bool(on)
 
     def giants_staging(self):
         p, n = C.c_void_p(), C.c_size_t()
@@ -186,6 +199,7 @@ class Engine:
     # ---- hot path
     def _take(self, n):
         n = min(n, self.cap)
+        self.payloads = [int(self._hits[i].reserved) for i in range(n)]
         return [(int(self._hits[i].code), int(self._hits[i].idx), int(self._hits[i].window)) for i in range(n)]
 
     def step(self, P_xy):

@@ -57,6 +57,19 @@ class Search:
             fin = ec.N - fin
         return fin
 
+    def check_verified(self, code, idx, j, payload):
+        """A record that survived device-side verification: the baby-step index b = payload is known, so
+        the candidates of checkerThread (1_9_7File.pb:4025-4124) are tried directly, without the htCPU table."""
+        base = self.window_key(j) + self.centerbig
+        giant = (idx + 1) * 2 * self.w
+        if code == 4 or payload == 0xFFFFFFFE:
+            return self._try(base + giant) or self._try(base - giant)
+        b = payload + 1
+        if code == 5:
+            return self._try(base + b) or self._try(base - b)
+        sgn = 1 if code == 1 else -1
+        return self._try(base + sgn * (giant + b)) or self._try(base + sgn * (giant - b))
+
     def check_hit(self, htcpu, code, idx, j):
         """Turn one record of this rank's window j into the private key (or None: false positive)."""
         base = self.window_key(j) + self.centerbig
@@ -98,9 +111,12 @@ def solve(engine, htcpu, T, B, p, w, htsz, pk, pke, target_xy, batch=16, rank=0,
     while done < nwin:
         chunk = min(nwin - done, 64 * batch)
         hits, d = engine.run(s.window_point(done), s.D, chunk, batch=min(batch, chunk), stop_after_hits=1)
-        for code, idx, win in hits:
+        for (code, idx, win), payload in zip(hits, list(engine.payloads)):
             seen += 1
-            key = s.check_hit(htcpu, code, idx, done + win)
+            if getattr(engine, "verify", False) and payload != 0xFFFFFFFF:
+                key = s.check_verified(code, idx, done + win, payload)
+            else:
+                key = s.check_hit(htcpu, code, idx, done + win)
             if key is not None:
                 return key, done + d, seen
         done += d

@@ -38,6 +38,10 @@ typedef struct bsgs_ctx bsgs_ctx;
  *   4: P.x == Q_idx.x and X(2P) probes true      5: P.x itself probes true (idx = 0)
  * `window` is the index of the base point inside a multi-window call (0 for bsgs_step). */
 typedef struct { uint32_t code, idx, window, reserved; } bsgs_hit;
+/* `reserved`: 0xFFFFFFFF unless the "verify" option is on.  With it, every record is re-examined on
+ * the device (full 256-bit X of P +- Q_idx against the recomputed baby point (j+1)G -- the work of
+ * checkerThread, F197:3933-4296): false positives of the 32-bit-tag table are dropped, surviving
+ * records carry the baby-step payload j (code 4: 0xFFFFFFFE, no table entry involved). */
 
 typedef enum {
     BSGS_OK = 0,
@@ -68,6 +72,9 @@ int  bsgs_giants_export(bsgs_ctx *ctx, void *g2, size_t bytes);
 /* `htgpu` = the bytes of <Gx>_<w>_<H>_htGPUv0.BIN as they are (4H + 4 + 4w bytes; F197:3337-3444).
  * Replaces cuMemcpyHtoD of *GpuHT (F197:2350). */
 int  bsgs_upload_ht(bsgs_ctx *ctx, const void *htgpu, size_t bytes);
+/* `htcpu` = the bytes of <Gx>_<w>_<H>_htCPUv0.BIN (4H + 4 + 8w bytes; F197:3232-3335): the same table
+ * together with its payloads j, which device-side verification ("verify" option) needs. */
+int  bsgs_upload_htcpu(bsgs_ctx *ctx, const void *htcpu, size_t bytes);
 /* Two-phase variants for multi-GPU start-up: obtain the device staging buffer (so that an NCCL
  * broadcast can land the image in place), then commit (build the in-HBM layouts). */
 int  bsgs_giants_staging(bsgs_ctx *ctx, void **dev_ptr, size_t *bytes);
@@ -124,7 +131,8 @@ int  bsgs_probe_keys(bsgs_ctx *ctx, const uint64_t *keys, uint64_t nkeys, uint8_
 /* geometry actually used by the kernel (threads, points per thread, bytes resident) */
 typedef struct { uint32_t grid, block, points_per_thread, sm_count; uint64_t n_giants, bytes_giants, bytes_chain, bytes_table; } bsgs_info;
 int  bsgs_get_info(const bsgs_ctx *ctx, bsgs_info *info);
-/* tuning knobs, call before uploads: "blocks_per_sm" (1..3 resident 256-thread CTAs per SM; the
+/* "verify" (0|1, any time; needs payloads: a device-side build or bsgs_upload_htcpu).
+ * tuning knobs, call before uploads: "blocks_per_sm" (1..3 resident 256-thread CTAs per SM; the
  * grid is SMs x this), "max_windows" (sizes the chain buffer), "l2_fetch" (32|64|128: device-wide
  * DRAM->L2 fetch granularity) */
 int  bsgs_set_option(bsgs_ctx *ctx, const char *name, int64_t value);

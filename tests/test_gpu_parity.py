@@ -495,3 +495,66 @@ def test_reupload_and_argument_errors(pkg, orc):
             e.ht_export("cpu")                                     # payloads unknown after a plain htGPU upload
         with pytest.raises(pkg.BsgsError):
             e.upload_giants(g2[:-64])
+
+
+# ------------------------------------------------------------------ device-side verification
+def test_verify_drops_false_positives_and_keeps_true_hits(pkg, orc):
+    """Real baby table + real giants: with verify=1 the records are exactly those of the raw launch whose
+    candidate X equals a baby point on all 256 bits (what checkerThread establishes on the CPU), each with
+    its payload j; planted 60-bit collisions (same bucket + tag, different point) are dropped."""
+    T, B, p, w, htsz = 32, 4, 8, 1 << 12, 6                          # load 64 per bucket: many tag candidates per probe
+    N = T * B * p
+    keys = orc.baby_keys(w)
+    rnd = random.Random(77)
+    # true hits: P = (m + (k+1)*2w)G  ->  P + Q_k = m*G with m in [1, w]  (code 1), and the mirrored code 2
+    k1, m1 = 17, 1234
+    k2, m2 = N - 1, 1
+    P1 = pyec.mul(pyec.G, m1 + (k1 + 1) * 2 * w)
+    P2 = pyec.mul(pyec.G, (pyec.N - m2 - (k2 + 1) * 2 * w) % pyec.N)       # P - Q_k = -(m2)G: X equals X(m2 G)
+    # false positives: overwrite some table keys with the 64-bit key of random candidates (same bucket+tag, other point)
+    Pf = random_point(rnd)
+    fake = [(1, 5), (2, 99), (1, 700)]
+    keys2 = keys.copy()
+    for i, (c, k) in enumerate(fake):
+        keys2[3000 + i] = np.uint64(candidate_x(Pf, w, k, c) & M64)
+    cpu, gpu = orc.build_ht(keys2, htsz)
+    g2 = orc.build_g2(T, B, p, w)
+    with pkg.Engine(T, B, p, w, htsz) as e:
+        e.upload_giants(g2); e.upload_htcpu(cpu)
+        assert bytes(e.ht_export("cpu")) == bytes(cpu) and bytes(e.ht_export("gpu")) == bytes(gpu)
+        for Ppt, want in ((P1, (1, k1, m1 - 1)), (P2, (2, k2, m2 - 1)), (Pf, None)):
+            e.set_verify(False)
+            raw = norm_hits(e.step(Ppt))
+            assert raw == norm_hits(orc.launch(g2, T, B, p, gpu, htsz, Ppt))
+            e.set_verify(True)
+            ver = e.step(Ppt); pay = list(e.payloads)
+            assert set(ver) <= set(raw)
+            if want:
+                assert (want[0], want[1]) in ver and pay[ver.index((want[0], want[1]))] == want[2]
+            else:
+                assert set(fake) <= set(raw) and not (set(fake) & set(ver))
+            for (c, i), pl in zip(ver, pay):                          # every survivor is a genuine 256-bit match
+                if c in (1, 2):
+                    assert candidate_x(Ppt, w, i, c) == pyec.mul(pyec.G, pl + 1)[0]
+
+
+def test_verify_codes_4_5_and_solve(pkg, orc):
+    T, B, p, w, htsz = 16, 4, 8, 1 << 14, 10
+    with pkg.Engine(T, B, p, w, htsz, verify=1) as e:
+        e.giants_generate(); e.ht_generate()
+        # code 5: P itself is a baby point; code 4: P == Q_k (doubling) -- handled without a table entry
+        Pb = pyec.mul(pyec.G, 4321)
+        hits = e.step(Pb)
+        assert (5, 0) in hits and e.payloads[hits.index((5, 0))] == 4320
+        k = 9
+        Q = giant(w, k)
+        hits = e.step(Q)
+        assert all(c != 4 or pl == 0xFFFFFFFE for (c, i), pl in zip(hits, e.payloads))
+        # whole problems through solve(): only verified records reach the host-side checker
+        rnd = random.Random(31)
+        pk = 1 << 36
+        for _ in range(4):
+            secret = pk + rnd.randrange(1, 1 << 35)
+            target = pyec.mul(pyec.G, secret)
+            key, done, seen = pkg.solve(e, None, T, B, p, w, htsz, pk, pk + (1 << 35), target)
+            assert key == secret and seen <= 2
