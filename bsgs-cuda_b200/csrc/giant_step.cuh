@@ -27,7 +27,14 @@
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include "fp.cuh"
+
+// GS_FP_HALF2 = 1: fingerprints are compared two at a time as fp16 pairs (HSET2.NE, one instruction
+// per word instead of three integer ones).  0 keeps the integer zero-halfword test.
+#ifndef GS_FP_HALF2
+#define GS_FP_HALF2 1
+#endif
 
 namespace gs {
 
@@ -117,8 +124,19 @@ __device__ __forceinline__ Fe lds_fe(const uint32_t* s) {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- fingerprint sectors ------------------------------------------------------------------------
-// 16 halfwords per bucket: fp[0..14] = tag >> 16 of the first 15 entries (0 when unused), last
+// 16 halfwords per bucket: fp[0..14] = fingerprint of the first 15 entries (0 when unused), last
 // halfword = entry count, 0xFFFF when the bucket holds more than 15.
+// Fingerprint of a 32-bit tag: its top 16 bits; in the half2 variant exponent bits 14..13 are forced
+// to 01 so that the pattern, read as an fp16 number, is a normal number (exponent 8..15: never
+// Inf/NaN, never zero or denormal, which the comparison may flush) -- bit-equal fingerprints then
+// always compare equal and distinct ones never do; empty slots (0) and the count match nothing.
+__host__ __device__ __forceinline__ uint32_t fpr16(uint32_t tag) {
+#if GS_FP_HALF2
+    return ((tag >> 16) & 0x9FFFu) | 0x2000u;
+#else
+    return tag >> 16;
+#endif
+}
 __global__ void k_build_fp_sectors(const uint32_t* __restrict__ off, const uint32_t* __restrict__ tags,
                                    uint4* __restrict__ sectors, uint64_t H, unsigned long long* overfull) {
     uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,8 +145,8 @@ __global__ void k_build_fp_sectors(const uint32_t* __restrict__ off, const uint3
     uint32_t wbuf[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        uint32_t a = (uint32_t)(2 * i) < n ? tags[lo + 2 * i] >> 16 : 0u;
-        uint32_t b = (uint32_t)(2 * i + 1) < n && i < 7 ? tags[lo + 2 * i + 1] >> 16 : 0u;
+        uint32_t a = (uint32_t)(2 * i) < n ? fpr16(tags[lo + 2 * i]) : 0u;
+        uint32_t b = (uint32_t)(2 * i + 1) < n && i < 7 ? fpr16(tags[lo + 2 * i + 1]) : 0u;
         wbuf[i] = a | (b << 16);
     }
     wbuf[7] = (wbuf[7] & 0xFFFFu) | ((n <= 15u ? n : 0xFFFFu) << 16);
@@ -152,17 +170,47 @@ struct FpSector {
     // true when the exact lookup is required: some halfword equals the fingerprint (this includes
     // chance matches with the count field or an empty slot -- harmless) or the bucket is over-full
     __device__ __forceinline__ bool maybe(uint32_t tag) const {
-        const uint32_t f = (tag >> 16) * 0x00010001u;
+        const uint32_t f = fpr16(tag) * 0x00010001u;
+#if GS_FP_HALF2
+        // ordered "both halves differ" per word; the over-full marker 0xFFFF is a NaN, for which the
+        // ordered comparison is false, so such a bucket always reports "maybe" (checked explicitly too)
+#define FP_NE(x) __hbne2(*reinterpret_cast<const __half2*>(&(x)), *reinterpret_cast<const __half2*>(&f))
+        const bool allne = FP_NE(a.x) & FP_NE(a.y) & FP_NE(a.z) & FP_NE(a.w) & FP_NE(b.x) & FP_NE(b.y) & FP_NE(b.z) & FP_NE(b.w);
+#undef FP_NE
+        return !allne;
+#else
         uint32_t acc = 0;
 #define FP_Z(x) { uint32_t y = (x) ^ f; acc |= (y - 0x00010001u) & ~y; }
         FP_Z(a.x) FP_Z(a.y) FP_Z(a.z) FP_Z(a.w) FP_Z(b.x) FP_Z(b.y) FP_Z(b.z) FP_Z(b.w)
 #undef FP_Z
         return ((acc & 0x80008000u) != 0u) | (b.w >= 0xFFFF0000u);
+#endif
     }
 };
 
 // exact, slow: Px == Qx (true doubling -> code 4), PTX197:L28996-
 __device__ __noinline__ uint64_t double_x_low64_v(Fe px, Fe inv2y) { return double_x_low64(px.v, inv2y.v); }
+
+// Rare half of the drain: everything about ring slot `slot` of a burst is recomputed from its chain
+// index cj = ci_first - slot/2 (row cj / W, window cj % W) -- whether the row is padding (giant index
+// >= N), whether the pair was a tangent (Px == Qx: slot 2j holds X(2P), code 4, and slot 2j+1 is
+// stale), whether the slot lies beyond the ragged last burst -- then the exact CSR lookup alone decides
+// (the fingerprint sector is only a filter in front of it)
+// (PTX197:L33723-34006).  Reached for a fingerprint match (2^-16 per table entry), an over-full
+// bucket, or when the burst contained any of the rare cases above.
+static __device__ __noinline__ void drain_slow(const Tables& tb, const uint32_t* s_win, int W, uint32_t t, int ci_first, int slot, int fill, uint64_t key) {
+    if (slot >= fill) return;
+    const int cj = ci_first - (slot >> 1), rj = cj / W, wj = cj - rj * W;
+    const bool plus = slot & 1;
+    const uint32_t idx = (uint32_t)rj * tb.NT + t;
+    if (idx >= tb.N) return;
+    const size_t NT2 = 2 * (size_t)tb.NT;
+    const Fe qx = ldg_fe(tb.gx + (size_t)rj * NT2 + t, tb.gx + (size_t)rj * NT2 + tb.NT + t);
+    const bool eq = fp::fe_eq(qx.v, s_win + wj * 32);
+    if (eq && plus) return;
+    const uint32_t h = (uint32_t)key & tb.mask, tag = (uint32_t)(key >> 32);
+    if (probe_csr(tb.csr_off, tb.csr_tags, h, tag)) record_hit(tb, plus ? 1u : (eq ? 4u : 2u), idx, (uint32_t)wj);
+}
 
 // MODE 0: probe every candidate X in the baby-step table and record hits (the giant-step search).
 // MODE 1: the same arithmetic used as a generator: the "giant" array holds (i+1)*G, the windows are
@@ -171,7 +219,7 @@ __device__ __noinline__ uint64_t double_x_low64_v(Fe px, Fe inv2y) { return doub
 //         (baby(), 1_9_7File.pb:1162-1235).
 template <int BLOCK, int MINB, int MODE>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_giant_step(const Tables tb, const __grid_constant__ WinParams wp, int W) {
+k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParams wp, int W) {
     __shared__ __align__(16) uint32_t s_win[kMaxW * 32];
     __shared__ uint64_t s_ring[MODE == 0 ? kRing * BLOCK : 1];
     const uint32_t t = blockIdx.x * BLOCK + threadIdx.x;
@@ -195,22 +243,28 @@ k_giant_step(const Tables tb, const __grid_constant__ WinParams wp, int W) {
     }
 
     // ---------------- PASS 1: running product of the denominators -> chain ----------------
+    // All addresses are running pointers (one 64-bit add per use): recomputing them from (r, w, ci)
+    // cost ~60 integer instructions per point-window, and every instruction beside an IMAD.WIDE
+    // costs issue time on this part.
+    const size_t NT2 = 2 * (size_t)NT;
     Fe acc; acc.v[0] = 1;
 #pragma unroll
     for (int i = 1; i < 8; i++) acc.v[i] = 0;
     {
-        int r = 0, w = 0;
-        const int total = PP * W;
+        const uint4* gxp = tb.gx + t;
+        uint4* cp = tb.chain + t;
 #pragma unroll 1
-        for (int ci = 0; ci < total; ci++) {
-            Fe qx = ldg_fe(tb.gx + (size_t)(2 * r) * NT + t, tb.gx + (size_t)(2 * r + 1) * NT + t);
-            Fe d;
-            { Fe px = lds_fe(s_win + w * 32); fp::fe_sub_canon(d.v, px.v, qx.v); }
-            if (fp::fe_is_zero_rare(d.v)) d = lds_fe(s_win + w * 32 + 24);          // 2*Py
-            Fe n; fp::fe_mul(n.v, acc.v, d.v); acc = n;
-            size_t co = (size_t)ci * 2 * NT + t;
-            st8_stream(tb.chain + co, tb.chain + co + NT, acc.v);
-            if (++w == W) { w = 0; r++; }
+        for (int r = 0; r < PP; r++, gxp += NT2) {
+            const Fe qx = ldg_fe(gxp, gxp + NT);
+            const uint32_t* sw = s_win;
+#pragma unroll 1
+            for (int w = 0; w < W; w++, sw += 32, cp += NT2) {
+                Fe d;
+                { Fe px = lds_fe(sw); fp::fe_sub_canon(d.v, px.v, qx.v); }
+                if (fp::fe_is_zero_rare(d.v)) d = lds_fe(sw + 24);                          // 2*Py
+                Fe n; fp::fe_mul(n.v, acc.v, d.v); acc = n;
+                st8_stream(cp, cp + NT, acc.v);
+            }
         }
     }
 
@@ -218,27 +272,34 @@ k_giant_step(const Tables tb, const __grid_constant__ WinParams wp, int W) {
     Fe inv; fp::fe_inv(inv.v, acc.v);                                // (a by-value wrapper keeps inv out of local memory but costs 3 spills at 80 registers: measured slower)
 
     // ---------------- PASS 2: unwind, slopes, X, keys -> ring -> probe bursts ----------------
-    int fill = 0, ci_first = 0; uint32_t eqmask = 0, deadmask = 0;
-    int r = PP - 1, w = W - 1;
+    // Loop-carried state is kept small (80 registers, 3 CTAs per SM): the giant index of the row, one
+    // pointer into the chain, the window-constant pointer (which doubles as the window counter) and
+    // the ring fill.  The rare cases -- a padding row (giant index >= N), a
+    // tangent (Px == Qx) or the ragged last burst -- only raise `special`; the drain then classifies
+    // every slot from its chain index (classify_slot) instead of the loop tracking per-slot masks.
+    int fill = 0;
+    bool special = false;
+    uint32_t kidx = (uint32_t)(PP - 1) * NT + t;                    // giant index of the current row
+    const uint4* cp = tb.chain + (size_t)(PP * W - 1) * NT2 + t;  // &chain[ci]; chain[ci-1] is one stride below
+    const uint32_t* const sw_top = s_win + (W - 1) * 32;
+    const uint32_t* sw = sw_top;
     Fe qx, qy;                                                     // the row's giant point, held across its windows
 #pragma unroll 1
     for (int ci = PP * W - 1; ci >= 0; ci--) {
-        const bool live = (uint32_t)r * NT + t < tb.N;
-        const uint32_t* sw = s_win + w * 32;
         Fe cprev;                                                  // chain[ci-1], or 1 for the very first element
+        cp -= NT2;
         if (ci > 0) {
-            size_t cp = (size_t)(ci - 1) * 2 * NT + t;
-            ld8_stream(cprev.v, tb.chain + cp, tb.chain + cp + NT);
-            if (ci > 1) { prefetch_l2(tb.chain + cp - 2 * (size_t)NT); prefetch_l2(tb.chain + cp - (size_t)NT); }
+            ld8_stream(cprev.v, cp, cp + NT);
+            if (ci > 1) { prefetch_l2(cp - NT2); prefetch_l2(cp - NT); }
         } else {
             cprev.v[0] = 1;
 #pragma unroll
             for (int i = 1; i < 8; i++) cprev.v[i] = 0;
         }
-        if (w == W - 1) {
-            const uint4* gxp = tb.gx + (size_t)(2 * r) * NT + t;
-            const uint4* gyp = tb.gy + (size_t)(2 * r) * NT + t;
-            qx = ldg_fe(gxp, gxp + NT); qy = ldg_fe(gyp, gyp + NT);
+        if (sw == sw_top) {                                         // new row: slot (r, t) lives at (2r)*NT + t = 2*kidx - t
+            const size_t go = 2 * (size_t)kidx - t;
+            qx = ldg_fe(tb.gx + go, tb.gx + go + NT); qy = ldg_fe(tb.gy + go, tb.gy + go + NT);
+            if (MODE == 0 && kidx >= tb.N) special = true;
         }
         Fe d;
         { Fe px = lds_fe(sw); fp::fe_sub_canon(d.v, px.v, qx.v); }
@@ -247,62 +308,63 @@ k_giant_step(const Tables tb, const __grid_constant__ WinParams wp, int W) {
         Fe invd;
         fp::fe_mul(invd.v, inv.v, cprev.v);                        // 1 / d_ci
         { Fe x; fp::fe_mul(x.v, inv.v, d.v); inv = x; }            // 1 / (d_0 ... d_{ci-1})
+        uint64_t* rp = ring + fill * BLOCK;
         if (!eq) {
-            Fe u, s = qy;
+            Fe u;
             { Fe npx = lds_fe(sw + 16); fp::fe_sub_canon(u.v, npx.v, qx.v); }                      // -(Px + Qx)
 #pragma unroll
-            for (int side = 0; side < 2; side++) {                  // side 0: P - Q (code 2), slope (Py + Qy)/d ; side 1: P + Q (code 1)
+            for (int side = 0; side < 2; side++) {                  // side 0: P - Q (code 2), slope (Py + Qy)/d ; side 1: P + Q (code 1), slope (Py - Qy)/d
                 Fe py = lds_fe(sw + 8), sum, lam, l2;
-                fp::fe_add_lazy(sum.v, py.v, s.v);
+                if (side == 0) fp::fe_add_lazy(sum.v, py.v, qy.v);
+                else fp::fe_sub_canon(sum.v, py.v, qy.v);
                 fp::fe_mul(lam.v, sum.v, invd.v);
                 fp::fe_sqr(l2.v, lam.v);
                 const uint64_t key = fp::fe_add_low64_canon(l2.v, u.v);
-                if (MODE == 0) ring[(fill + side) * BLOCK] = key;
-                else if (live) {                                    // multiplier C - (i+1) (side 0) or C + (i+1) (side 1)
-                    const uint64_t i1 = (uint64_t)r * NT + t + 1, c = wp.center[w];
+                if (MODE == 0) rp[side * BLOCK] = key;
+                else if (kidx < tb.N) {                             // multiplier C - (i+1) (side 0) or C + (i+1) (side 1)
+                    const uint64_t i1 = (uint64_t)kidx + 1, c = wp.center[(sw - s_win) >> 5];
                     const uint64_t m = side == 0 ? c - i1 : c + i1;
                     if (m <= tb.nkeys) tb.keys_out[m - 1] = key;
-                }
-                if (side == 0) {                                    // Py - Qy = Py + (p - Qy); Qy != 0 on this curve
-                    const uint32_t z[8] = {FP_P0, FP_P1, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-                    fp::fe_sub_canon(s.v, z, qy.v);
                 }
             }
         } else {
             Fe px = lds_fe(sw);
             const uint64_t key = double_x_low64_v(px, invd);        // X(2P)  (code 4); cannot occur in emit mode
-            if (MODE == 0) ring[fill * BLOCK] = key;
+            if (MODE == 0) rp[0] = key;
+            special = true;
         }
-        if (MODE == 1) { if (--w < 0) { w = W - 1; r--; } continue; }
-        if (fill == 0) ci_first = ci;
-        eqmask |= (eq ? 1u : 0u) << (fill >> 1);
-        deadmask |= (live ? 0u : 1u) << (fill >> 1);
-        fill += 2;
-        if (fill == kRing || ci == 0) {
-            // drain: slot 2j / 2j+1 = minus / plus key of chain index ci_first - j
+        if (MODE == 0) {
+            fill += 2;
+            if (fill == kRing || ci == 0) {
+                // drain: slot 2j / 2j+1 = minus / plus key of chain index ci_first - j
+                const int ci_first = ci + (fill >> 1) - 1;
+                if (ci == 0) special = true;                        // the last burst may end inside a group of four
 #pragma unroll 1
-            for (int s0 = 0; s0 < fill; s0 += 4) {
-                FpSector sec[4]; uint64_t key[4];
+                for (int s0 = 0; s0 < fill; s0 += 4) {
+                    FpSector sec[4]; uint64_t key[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    key[j] = ring[(s0 + j) * BLOCK];
-                    sec[j].load(tb, (uint32_t)key[j] & tb.mask);
-                }
+                    for (int j = 0; j < 4; j++) {
+                        key[j] = ring[(s0 + j) * BLOCK];
+                        sec[j].load(tb, (uint32_t)key[j] & tb.mask);
+                    }
+                    uint32_t need = special ? 15u : 0u;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int pair = (s0 + j) >> 1; const bool plus = (s0 + j) & 1;
-                    const bool eqj = (eqmask >> pair) & 1u, dead = (deadmask >> pair) & 1u;
-                    if (s0 + j >= fill || dead || (plus && eqj)) continue;
-                    const uint32_t tag = (uint32_t)(key[j] >> 32);
-                    if (sec[j].maybe(tag) && probe_csr(tb.csr_off, tb.csr_tags, (uint32_t)key[j] & tb.mask, tag)) {
-                        const int cj = ci_first - pair, rj = cj / W, wj = cj - rj * W;
-                        record_hit(tb, plus ? 1u : (eqj ? 4u : 2u), (uint32_t)rj * NT + t, (uint32_t)wj);
+                    for (int j = 0; j < 4; j++) need |= (sec[j].maybe((uint32_t)(key[j] >> 32)) ? 1u : 0u) << j;
+                    // One warp-wide vote per group; the rare branch ends in an explicit __syncwarp(): without
+                    // it lanes that took the out-of-line path were observed (ncu: 31.93 active lanes in the
+                    // arithmetic, one SM busy 3x longer than the rest) to stay split from their warp for the
+                    // remainder of the loop.
+                    if (__any_sync(0xFFFFFFFFu, need != 0u)) {
+#pragma unroll 1
+                        for (int j = 0; j < 4; j++)
+                            if ((need >> j) & 1u) drain_slow(tb, s_win, W, t, ci_first, s0 + j, fill, key[j]);
+                        __syncwarp();
                     }
                 }
+                fill = 0; special = false;
             }
-            fill = 0; eqmask = 0; deadmask = 0;
         }
-        if (--w < 0) { w = W - 1; r--; }
+        if (sw == s_win) { sw = sw_top; kidx -= NT; } else sw -= 32;
     }
 }
 

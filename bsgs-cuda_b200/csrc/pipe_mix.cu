@@ -9,12 +9,12 @@
 #define CH 8
 __constant__ uint32_t cb[64];
 
-// KIND: 0 IADD3, 1 SHF (funnel shift), 2 IMAD.LO, 3 SETP+SEL
+// KIND: 0 IADD3, 1 SHF (funnel shift), 2 IMAD.LO, 3 SETP+SEL; KIND2 additionally 4 FFMA, 5 DFMA, 6 HSET2 (fp16x2 compare)
 template <int NW, int NB, int KIND, int NB2 = 0, int KIND2 = 0>
 __global__ void __launch_bounds__(1024, 1) mix(uint64_t* out, uint32_t seed, long long* cycles) {
-    uint64_t acc[CH]; uint32_t x[CH], y[CH], mm[CH]; float f[CH];
+    uint64_t acc[CH]; uint32_t x[CH], y[CH], mm[CH]; float f[CH]; double df[CH];
 #pragma unroll
-    for (int i = 0; i < CH; i++) { acc[i] = (uint64_t)(i + seed) * 0x9E3779B97F4A7C15ull + threadIdx.x; x[i] = i * 7 + seed + threadIdx.x * 31; y[i] = x[i] * 3; f[i] = 1.0f + i; mm[i] = (i + 3) * 0x85EBCA6Bu + threadIdx.x * 977 + seed; }
+    for (int i = 0; i < CH; i++) { acc[i] = (uint64_t)(i + seed) * 0x9E3779B97F4A7C15ull + threadIdx.x; x[i] = i * 7 + seed + threadIdx.x * 31; y[i] = x[i] * 3; f[i] = 1.0f + i; df[i] = 1.0 + i; mm[i] = (i + 3) * 0x85EBCA6Bu + threadIdx.x * 977 + seed; }
     uint32_t a = seed + threadIdx.x;
     long long t0 = clock64();
 #pragma unroll 8
@@ -37,13 +37,15 @@ __global__ void __launch_bounds__(1024, 1) mix(uint64_t* out, uint32_t seed, lon
                 if (KIND2 == 0) asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(y[i]) : "r"(mm[(i + 2) % CH]), "r"(a));
                 if (KIND2 == 1) asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(y[i]) : "r"(mm[(i + 2) % CH]));
                 if (KIND2 == 4) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(1.0001f), "f"(0.5f));
+                if (KIND2 == 5) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(df[i]) : "d"(1.0001), "d"(0.5));
+                if (KIND2 == 6) asm volatile("set.ne.u32.f16x2 %0, %0, %1;" : "+r"(y[i]) : "r"(mm[(i + 2) % CH]));
             }
         }
     }
     long long t1 = clock64();
     uint64_t s = 0;
 #pragma unroll
-    for (int i = 0; i < CH; i++) s += acc[i] + x[i] + y[i] + (uint64_t)f[i];
+    for (int i = 0; i < CH; i++) s += acc[i] + x[i] + y[i] + (uint64_t)f[i] + (uint64_t)df[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -93,7 +95,15 @@ int main() {
     run<0, 0, 0, 2, 4>("ffma_2", sms, out, cyc, false);
     run<1, 0, 0, 1, 4>("wide1_ffma_1", sms, out, cyc, false);
     run<1, 0, 0, 2, 4>("wide1_ffma_2", sms, out, cyc, false);
-    run<2, 3, 0>("wide2_iadd3_3", sms, out, cyc, true);
+    run<2, 3, 0>("wide2_iadd3_3", sms, out, cyc, false);
+    run<0, 0, 0, 1, 5>("dfma_1", sms, out, cyc, false);
+    run<1, 0, 0, 1, 5>("wide1_dfma_1", sms, out, cyc, false);
+    run<1, 0, 0, 2, 5>("wide1_dfma_2", sms, out, cyc, false);
+    run<1, 2, 0, 1, 5>("wide1_iadd3_2_dfma_1", sms, out, cyc, false);
+    run<0, 2, 0, 1, 5>("iadd3_2_dfma_1", sms, out, cyc, false);
+    run<0, 0, 0, 1, 6>("hset2_1", sms, out, cyc, false);
+    run<1, 0, 0, 1, 6>("wide1_hset2_1", sms, out, cyc, false);
+    run<1, 0, 0, 2, 6>("wide1_hset2_2", sms, out, cyc, true);
     printf("}\n");
     return 0;
 }
