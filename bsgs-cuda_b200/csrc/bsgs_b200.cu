@@ -124,6 +124,10 @@ extern "C" int bsgs_set_option(bsgs_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "verify")) { ctx->verify = value != 0; return BSGS_OK; }      // may be toggled at any time
     if (ctx->d_gx || ctx->d_buckets) return BSGS_E_STATE;       // geometry is baked into the layouts
     if (!strcmp(name, "blocks_per_sm")) { if (value < 1 || value > 3) return BSGS_E_ARG; ctx->blocks_per_sm = (uint32_t)value; compute_geometry(ctx); return BSGS_OK; }
+    if (!strcmp(name, "block")) {                               // threads per CTA: 256 (x blocks_per_sm) or 320 (x 2)
+        if (value != 256 && value != 320) return BSGS_E_ARG;
+        ctx->block = (uint32_t)value; if (value == 320) ctx->blocks_per_sm = 2; compute_geometry(ctx); return BSGS_OK;
+    }
     if (!strcmp(name, "max_windows")) { if (value < 1 || value > BSGS_MAX_WINDOWS) return BSGS_E_ARG; ctx->max_windows = (uint32_t)value; return BSGS_OK; }
     if (!strcmp(name, "l2_fetch")) {                            // device-wide: DRAM->L2 fetch granularity for the random sector reads
         if (value != 32 && value != 64 && value != 128) return BSGS_E_ARG;
@@ -313,10 +317,14 @@ extern "C" int bsgs_ht_build_from_keys(bsgs_ctx* ctx, const uint64_t* keys, uint
 // The real baby-step table: key j = low 64 bits of X((j+1)G), j < w (baby(), F197:1162-1235; index base
 // F197:1221), produced by the giant-step kernel in emit mode: a temporary array of (i+1)G, i < N,
 // and centres C_c = c(2N+1) + N + 1, so that centre c yields the multipliers c(2N+1)+1 .. (c+1)(2N+1).
-template <int MINB>
-static cudaError_t launch_emit(const bsgs_ctx* c, const gs::Tables& tb, const gs::WinParams& wp, int nwin) {
-    gs::k_giant_step<256, MINB, 1><<<c->grid, 256, 0, c->stream>>>(tb, wp, nwin);
+template <int BLOCK, int MINB>
+static cudaError_t launch_emit_k(const bsgs_ctx* c, const gs::Tables& tb, const gs::WinParams& wp, int nwin) {
+    gs::k_giant_step<BLOCK, MINB, 1><<<c->grid, BLOCK, 0, c->stream>>>(tb, wp, nwin);
     return cudaGetLastError();
+}
+static cudaError_t launch_emit(const bsgs_ctx* c, const gs::Tables& tb, const gs::WinParams& wp, int nwin) {
+    if (c->block == 320) return launch_emit_k<320, 2>(c, tb, wp, nwin);
+    return c->blocks_per_sm >= 3 ? launch_emit_k<256, 3>(c, tb, wp, nwin) : launch_emit_k<256, 2>(c, tb, wp, nwin);
 }
 static int generate_baby_keys(bsgs_ctx* ctx, uint64_t* d_keys) {
     size_t slots = (size_t)ctx->NT * ctx->PP;
@@ -345,7 +353,7 @@ static int generate_baby_keys(bsgs_ctx* ctx, uint64_t* d_keys) {
             wp.center[i] = (c0 + i) * span + ctx->N + 1;
             hec::pt_add(P, P, S);
         }
-        e = ctx->blocks_per_sm >= 3 ? launch_emit<3>(ctx, tb, wp, (int)n) : launch_emit<2>(ctx, tb, wp, (int)n);
+        e = launch_emit(ctx, tb, wp, (int)n);
         if (e != cudaSuccess) { ctx->last_cuda = (int)e; cudaGetLastError(); rc = BSGS_E_CUDA; }
     }
     e = cudaStreamSynchronize(ctx->stream);
@@ -435,6 +443,7 @@ static cudaError_t launch_k(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
 }
 static cudaError_t launch_any(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
     if (nwin < 1 || nwin > BSGS_MAX_WINDOWS) return cudaErrorInvalidValue;
+    if (c->block == 320) return launch_k<320, 2>(c, nwin, pxy);                        // 5 warps per scheduler, 96 registers
     switch (c->blocks_per_sm) {
         case 1: case 2: return launch_k<256, 2>(c, nwin, pxy);
         case 3: return launch_k<256, 3>(c, nwin, pxy);
