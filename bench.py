@@ -279,19 +279,31 @@ def run_reference(args):
             "config": {"workload": wl["name"], "T": T, "B": B, "p": p, "w": w, "htsz": htsz}, "cpu_baseline": cpu}
     if os.path.exists(orc.REF_LIB) and os.path.exists(orc.REF_CUBIN):
         ref = orc.RefKernel(T, B, p, w, htsz)
-        ref.upload_giants(e.giants_export())
+        g2 = e.giants_export()
+        ref.upload_giants(g2)
         ptr, nbytes = e.ht_device_image(); ref.upload_ht_dev(ptr, nbytes)
+        dropin_cubin = os.path.join(ROOT, "bsgs-cuda_b200", "dropin_test1.cubin")
+        mine = None
+        if args.with_dropin and os.path.exists(dropin_cubin):         # boundary option A: our module behind the reference's own interface
+            mine = orc.RefKernel(T, B, p, w, htsz, cubin=dropin_cubin)
+            mine.upload_giants(g2); mine.upload_ht_dev(ptr, nbytes)
         e.close()
-        ref.time_launches(pts[0], W)
-        ms = 0.0
-        for i in range(K):
-            ms += ref.time_launches(pts[i % len(pts)], 1)
+
+        def timed(k):
+            k.time_launches(pts[0], W)
+            return sum(k.time_launches(pts[i % len(pts)], 1) for i in range(K))
+        ms = timed(ref)
         value = 2 * N * K / (ms * 1e-3)
         line.update({"value": value, "ms_per_step": ms / K, "gpu_launches": K,
                      "reference_kind": "the reference's own GPU kernel _test1 (PTX from 1_9_7File.pb, ptxas -arch=sm_100a) on this box, 1 GPU; "
                                        "the reference has no CPU giant-step loop, see cpu_baseline for the CPU restatement",
                      "e2e": {"value": value, "unit": "giant-steps/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": 4}})
         ref.close()
+        if mine is not None:
+            ms2 = timed(mine)
+            line["dropin_module"] = {"value": 2 * N * K / (ms2 * 1e-3), "unit": "giant-steps/s", "ms_per_step": ms2 / K,
+                                     "what": "bsgs-cuda_b200/dropin_test1.cubin (entry _test1, const _A, the reference memory map) in the same harness, same tables, one window per launch"}
+            mine.close()
     else:
         e.close()
         line.update({"value": cpu["value"], "ms_per_step": None, "gpu_launches": 0,
@@ -315,6 +327,7 @@ def main():
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--with-dropin", action="store_true", help="reference arm only: also time bsgs-cuda_b200/dropin_test1.cubin in the same harness (extra key, off by default)")
     args = ap.parse_args()
     line = run_reference(args) if args.impl == "reference" else run_b200(args)
     if line is not None:

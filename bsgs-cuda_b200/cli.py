@@ -150,6 +150,23 @@ def read_pubs(o):
     return [o["pb"]]
 
 
+def list_devices(log):
+    """The start-up device listing with the parameter suggestion (1_9_7File.pb:778-860, Tune 324-431)."""
+    from . import native, tune
+    for d in native.devices():
+        log(f"Cuda device:{d['name']} ({d['free_bytes'] / 1048576:.3f}/{d['total_bytes'] // 1048576}MB)")
+        cores = tune.cores_for(d["cc"][0], d["cc"][1], d["sm_count"])
+        log(f"Device have: MP:{d['sm_count']} Cores+{cores}")
+        if d["sm_count"] and cores:
+            ref = tune.tune_reference(d["free_bytes"], d["sm_count"], cores, ncpu=os.cpu_count() or 1)
+            if ref:
+                log(tune.format_try(ref) + "   (reference Tune)")
+            own = tune.tune_b200(d["free_bytes"], d["sm_count"])
+            if own:
+                log(tune.format_try(own) + "   (this build)")
+        log("---------------")
+
+
 def main(argv=None, out=sys.stdout) -> int:
     log = lambda s: (out.write(s + "\n"), out.flush())               # noqa: E731
     try:
@@ -160,6 +177,10 @@ def main(argv=None, out=sys.stdout) -> int:
     except UsageError as ex:
         log(str(ex)); return 2
     o["devices"] = [int(x) for x in o["d"].split(",") if x != ""]
+    try:
+        list_devices(log)
+    except Exception as ex:                                            # noqa: BLE001 -- the listing is informational
+        log(f"device listing unavailable: {ex}")
     T, B, p, w, htsz = o["t"], o["b"], o["p"], o["w"], o["htsz"]
     fp = fingerprint(o)
     log(f"Current config hash[{fp}]")

@@ -136,6 +136,29 @@ extern "C" int bsgs_set_option(bsgs_ctx* ctx, const char* name, int64_t value) {
     return BSGS_E_ARG;
 }
 
+extern "C" int bsgs_device_count(int* count) {
+    if (!count) return BSGS_E_ARG;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; cudaGetLastError(); return BSGS_E_CUDA; }
+    return BSGS_OK;
+}
+extern "C" int bsgs_device_query(int device, bsgs_devinfo* out) {
+    if (!out) return BSGS_E_ARG;
+    memset(out, 0, sizeof *out);
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return BSGS_E_CUDA; }
+    if (device < 0 || device >= n) return BSGS_E_ARG;
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, device) != cudaSuccess) { cudaGetLastError(); return BSGS_E_CUDA; }
+    strncpy(out->name, pr.name, sizeof out->name - 1);
+    out->cc_major = pr.major; out->cc_minor = pr.minor; out->sm_count = pr.multiProcessorCount;
+    size_t fr = 0, tot = 0;
+    int cur = 0; cudaGetDevice(&cur);
+    if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); cudaSetDevice(cur); return BSGS_E_CUDA; }
+    cudaSetDevice(cur);
+    out->free_bytes = fr; out->total_bytes = tot;
+    return BSGS_OK;
+}
 extern "C" int bsgs_get_info(const bsgs_ctx* ctx, bsgs_info* info) {
     if (!ctx || !info) return BSGS_E_ARG;
     info->grid = ctx->grid; info->block = ctx->block; info->points_per_thread = ctx->PP; info->sm_count = (uint32_t)ctx->sm_count;

@@ -29,10 +29,15 @@ class Info(C.Structure):
                 ("n_giants", C.c_uint64), ("bytes_giants", C.c_uint64), ("bytes_chain", C.c_uint64), ("bytes_table", C.c_uint64)]
 
 
+class DevInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 128), ("cc_major", C.c_int32), ("cc_minor", C.c_int32), ("sm_count", C.c_int32), ("reserved", C.c_int32),
+                ("free_bytes", C.c_uint64), ("total_bytes", C.c_uint64)]
+
+
 EXPORTS = ["bsgs_create", "bsgs_destroy", "bsgs_strerror", "bsgs_last_cuda_error", "bsgs_upload_giants", "bsgs_upload_ht", "bsgs_upload_htcpu",
            "bsgs_giants_staging", "bsgs_giants_commit", "bsgs_ht_staging", "bsgs_ht_commit", "bsgs_step", "bsgs_step_multi",
            "bsgs_giants_generate", "bsgs_giants_export", "bsgs_ht_build_from_keys", "bsgs_ht_generate", "bsgs_ht_build_synthetic", "bsgs_ht_export", "bsgs_ht_device_image",
-           "bsgs_run", "bsgs_time_launches", "bsgs_probe_bench", "bsgs_probe_keys", "bsgs_get_info", "bsgs_set_option", "bsgs_debug_field"]
+           "bsgs_run", "bsgs_time_launches", "bsgs_probe_bench", "bsgs_probe_keys", "bsgs_get_info", "bsgs_set_option", "bsgs_debug_field", "bsgs_device_count", "bsgs_device_query"]
 
 _lib = None
 
@@ -75,8 +80,29 @@ def load():
     L.bsgs_get_info.argtypes = [vp, C.POINTER(Info)]
     L.bsgs_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.bsgs_debug_field.argtypes = [C.c_int, C.c_int, vp, vp, vp, u32]
+    L.bsgs_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.bsgs_device_query.argtypes = [C.c_int, C.POINTER(DevInfo)]
     _lib = L
     return L
+
+
+def devices():
+    """The device listing of the reference's start-up (1_9_7File.pb:778-860): name, compute
+    capability, multiprocessors, free/total memory of every CUDA device."""
+    L = load()
+    n = C.c_int()
+    rc = L.bsgs_device_count(C.byref(n))
+    if rc:
+        raise BsgsError(rc, "bsgs_device_count")
+    out = []
+    for i in range(n.value):
+        d = DevInfo()
+        rc = L.bsgs_device_query(i, C.byref(d))
+        if rc:
+            raise BsgsError(rc, "bsgs_device_query")
+        out.append({"index": i, "name": d.name.decode(), "cc": (d.cc_major, d.cc_minor), "sm_count": d.sm_count,
+                    "free_bytes": d.free_bytes, "total_bytes": d.total_bytes})
+    return out
 
 
 def debug_field(op: int, a, b, device=0):

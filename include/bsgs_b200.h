@@ -131,9 +131,16 @@ int  bsgs_probe_keys(bsgs_ctx *ctx, const uint64_t *keys, uint64_t nkeys, uint8_
 /* geometry actually used by the kernel (threads, points per thread, bytes resident) */
 typedef struct { uint32_t grid, block, points_per_thread, sm_count; uint64_t n_giants, bytes_giants, bytes_chain, bytes_table; } bsgs_info;
 int  bsgs_get_info(const bsgs_ctx *ctx, bsgs_info *info);
+/* device listing used by the parameter suggestion (`Tune`, 1_9_7File.pb:324-431): what the reference
+ * reads with cuDeviceGetName / cuDeviceComputeCapability / cuDeviceGetAttribute(16) / cuMemGetInfo_v2
+ * before it prints "Cuda device: ... Device have: MP:.. Cores+.." (1_9_7File.pb:778-860).  Needs no
+ * context; returns BSGS_E_ARG for a device index that does not exist. */
+typedef struct { char name[128]; int32_t cc_major, cc_minor, sm_count, reserved; uint64_t free_bytes, total_bytes; } bsgs_devinfo;
+int  bsgs_device_count(int *count);
+int  bsgs_device_query(int device, bsgs_devinfo *out);
 /* "verify" (0|1, any time; needs payloads: a device-side build or bsgs_upload_htcpu).
  * tuning knobs, call before uploads: "blocks_per_sm" (1..3 resident 256-thread CTAs per SM; the
- * grid is SMs x this), "max_windows" (sizes the chain buffer), "l2_fetch" (32|64|128: device-wide
+ * grid is SMs x this), "block" (256, or 320 = two 320-thread CTAs per SM), "max_windows" (sizes the chain buffer), "l2_fetch" (32|64|128: device-wide
  * DRAM->L2 fetch granularity) */
 int  bsgs_set_option(bsgs_ctx *ctx, const char *name, int64_t value);
 

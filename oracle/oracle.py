@@ -246,9 +246,12 @@ class SearchState:
 class RefKernel:
     """The reference's own `_test1` cubin driven through oracle/ref_harness.c."""
 
-    def __init__(self, T, B, p, w, htsz, dev=0):
-        if not (os.path.exists(REF_LIB) and os.path.exists(REF_CUBIN)):
-            raise FileNotFoundError("oracle/_ref not built (needs the reference tree at build time)")
+    def __init__(self, T, B, p, w, htsz, dev=0, cubin=None):
+        """cubin=None: the reference's kernel; otherwise any module with the same interface (entry
+        `_test1`, const `_A`, the reference memory map), e.g. bsgs-cuda_b200/dropin_test1.cubin."""
+        cubin = cubin or REF_CUBIN
+        if not (os.path.exists(REF_LIB) and os.path.exists(cubin)):
+            raise FileNotFoundError(f"{REF_LIB} / {cubin} not built (the reference cubin needs the reference tree at build time)")
         self.L = C.CDLL(REF_LIB)
         self.L.ref_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32]
         self.L.ref_upload_giants.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -258,7 +261,7 @@ class RefKernel:
         self.L.ref_upload_ht_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t]
         self.L.ref_time_launches.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_float)]
         self.h = C.c_void_p()
-        rc = self.L.ref_create(C.byref(self.h), dev, REF_CUBIN.encode(), T, B, p, w, htsz)
+        rc = self.L.ref_create(C.byref(self.h), dev, cubin.encode(), T, B, p, w, htsz)
         if rc:
             raise RuntimeError(f"ref_create failed: {rc}")
 

@@ -3,6 +3,7 @@ import ctypes
 import glob
 import os
 import re
+import pytest
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -54,3 +55,29 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 assert "oracle" not in open(os.path.join(root, f), errors="replace").read().replace("CPU oracle", "").replace("oracle's", "").lower().replace("the oracle", ""), f
+
+
+def test_dropin_module_exports_the_reference_kernel_interface():
+    """Option A of the boundary: the module must export `.entry _test1(.param .u64)` and a 120-byte
+    `.const _A` (cuModuleGetFunction / cuModuleGetGlobal_v2 by these names, 1_9_7File.pb:2198, 2278)."""
+    import re
+    ptx = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bsgs-cuda_b200", "dropin_test1.ptx")
+    if not os.path.exists(ptx):
+        pytest.skip("dropin_test1.ptx not built")
+    text = open(ptx).read()
+    assert re.search(r"\.visible \.entry _test1\(\s*\.param \.u64[^,)]*\)", text)
+    assert re.search(r"\.const \.align \d+ \.b8 _A\[120\];", text)
+    assert ".target sm_100a" in text
+
+
+def test_datasection_writer_round_trip(tmp_path):
+    """scripts/make_datasection.py embeds the module the way the reference embeds its own kernel
+    (XOR 93, Data.q quadwords, 1_9_7File.pb:4739-4741, 5181-23979); decoding gives the PTX back."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_datasection", os.path.join(root, "scripts", "make_datasection.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    ptx = b"//\n.version 8.8\n.target sm_100a\n.visible .entry _test1(.param .u64 p){ret;}\n"
+    text = m.encode(ptx)
+    assert text.startswith("DataSection") and "BSGS4_cuda_quad_htchangeble_v2:" in text
+    assert m.decode(text).rstrip(b"\0") == ptx

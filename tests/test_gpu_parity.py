@@ -219,6 +219,82 @@ def test_reference_kernel_codes_4_5(pkg, orc):
             assert norm_hits(e.step(Ppt)) == r_hits
 
 
+# ------------------------------------------------------------------ the drop-in module (boundary option A)
+DROPIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bsgs-cuda_b200", "dropin_test1.cubin")
+
+
+def _harness_available(orc):
+    return os.path.exists(orc.REF_LIB) and os.path.exists(DROPIN)
+
+
+@pytest.mark.parametrize("case", [(32, 4, 16, 4096, 10), (64, 20, 100, 60000, 14), (128, 2, 8, 5000, 4), (512, 8, 6, 30000, 13), (256, 3, 1, 3000, 9)])
+def test_dropin_module_matches_oracle_and_reference_kernel(orc, case):
+    """bsgs-cuda_b200/dropin_test1.cubin exports the reference kernel's own interface (`_test1`, `_A`,
+    the memory map of cuda(), 1_9_7File.pb:2181-2509): loaded by the same driver-API harness that
+    runs the reference's PTX it must produce the same (code, idx) records."""
+    if not _harness_available(orc):
+        pytest.skip("harness or drop-in module not built")
+    T, B, p, w, htsz = case
+    Ppt, plant, cpu, gpu, g2 = build_case(orc, T, B, p, w, htsz, seed=977 + T)
+    mine = orc.RefKernel(T, B, p, w, htsz, cubin=DROPIN)
+    mine.upload(g2, gpu)
+    ref = None
+    if _ref_available(orc):
+        ref = orc.RefKernel(T, B, p, w, htsz); ref.upload(g2, gpu)
+    rnd = random.Random(6)
+    for pt in [Ppt] + [random_point(rnd) for _ in range(2)]:
+        m_hits, m_count, _ = mine.launch(pt)
+        assert m_hits == norm_hits(orc.launch(g2, T, B, p, gpu, htsz, pt))
+        if ref is not None:
+            r_hits, r_count, _ = ref.launch(pt)
+            assert m_hits == r_hits and m_count == r_count
+    assert set(plant) <= set(mine.launch(Ppt)[0])
+    mine.close()
+    if ref is not None:
+        ref.close()
+
+
+def test_dropin_module_codes_4_5_and_repeat_launches(orc):
+    if not _harness_available(orc):
+        pytest.skip("harness or drop-in module not built")
+    T, B, p, w, htsz = 32, 4, 8, 2000, 8
+    N = T * B * p
+    g2 = orc.build_g2(T, B, p, w)
+    for k, sign in ((5, 1), (N - 1, -1)):
+        Q = giant(w, k)
+        Ppt = Q if sign > 0 else pyec.neg(Q)
+        dbl = pyec.add(Ppt, Ppt)
+        cpu, gpu = orc.build_ht(synthetic_keys(w, [dbl[0], Ppt[0]], k), htsz)
+        mine = orc.RefKernel(T, B, p, w, htsz, cubin=DROPIN); mine.upload(g2, gpu)
+        first, _, _ = mine.launch(Ppt)
+        again, _, _ = mine.launch(Ppt)                                 # the giant and chain blocks survive a launch
+        mine.close()
+        assert (4, k) in first and (5, 0) in first
+        assert first == again == norm_hits(orc.launch(g2, T, B, p, gpu, htsz, Ppt))
+
+
+def test_dropin_module_record_area_is_bounded(orc):
+    """More than 240 hits: the counter keeps counting, the giants just above the record area stay
+    intact (the reference overwrites them, 1_9_7File.pb:2337) -- a second launch still agrees."""
+    if not _harness_available(orc):
+        pytest.skip("harness or drop-in module not built")
+    T, B, p, w, htsz = 64, 4, 8, 4000, 8
+    N = T * B * p
+    g2 = orc.build_g2(T, B, p, w)
+    rnd = random.Random(11)
+    Ppt = random_point(rnd)
+    planted = [candidate_x(Ppt, w, k, 1 + (k & 1)) for k in range(0, 600, 2)]
+    cpu, gpu = orc.build_ht(synthetic_keys(w, planted, 3), htsz)
+    expect = norm_hits(orc.launch(g2, T, B, p, gpu, htsz, Ppt, cap=4096))
+    assert len(expect) >= 300
+    mine = orc.RefKernel(T, B, p, w, htsz, cubin=DROPIN); mine.upload(g2, gpu)
+    got, count, _ = mine.launch(Ppt)
+    assert count == len(expect) and len(got) == 240 and set(got) <= set(expect)
+    got2, count2, _ = mine.launch(Ppt)
+    assert count2 == count and set(got2) <= set(expect)
+    mine.close()
+
+
 # ------------------------------------------------------------------ whole problems
 def test_solve_small_range_true_tables(pkg, orc):
     """Real baby table + giants (built by the oracle on the CPU), key recovered through bsgs_run."""
@@ -558,3 +634,16 @@ def test_verify_codes_4_5_and_solve(pkg, orc):
             target = pyec.mul(pyec.G, secret)
             key, done, seen = pkg.solve(e, None, T, B, p, w, htsz, pk, pk + (1 << 35), target)
             assert key == secret and seen <= 2
+
+
+def test_device_listing_and_suggestion(pkg):
+    """bsgs_device_query + the Tune mirror: what the reference prints at start-up (1_9_7File.pb:778-860)."""
+    from bsgs_cuda_b200 import native, tune, cli
+    devs = native.devices()
+    assert devs and devs[0]["sm_count"] > 0 and 0 < devs[0]["free_bytes"] <= devs[0]["total_bytes"]
+    lines = []
+    cli.list_devices(lines.append)
+    assert lines[0].startswith("Cuda device:") and lines[1].startswith("Device have: MP:")
+    assert any(l.startswith("Try -t ") and "(this build)" in l for l in lines)
+    s = tune.tune_b200(devs[0]["free_bytes"], devs[0]["sm_count"])
+    assert s["device_mb"] * 1048576 < devs[0]["free_bytes"]
