@@ -41,3 +41,18 @@ def synthetic_keys(w, planted_x, seed):
 def norm_hits(hits):
     """sorted multiset of (code, idx) with the idx of code 5 forced to 0 (never written by the reference)."""
     return sorted((c, 0 if c == 5 else i) for c, i in hits)
+
+
+def build_case(orc, T, B, p, w, htsz, seed, nplant=24):
+    rnd = random.Random(seed)
+    N = T * B * p
+    Ppt = random_point(rnd)
+    plant = []
+    for i in range(nplant):
+        k = rnd.randrange(N) if i > 3 else (0, N - 1, N // 2, 1 % N)[i]
+        plant.append((1 + (i & 1), k))
+    xs = [candidate_x(Ppt, w, k, c) for c, k in plant]
+    keys = synthetic_keys(w, xs, seed)
+    cpu, gpu = orc.build_ht(keys, htsz)
+    g2 = orc.build_g2(T, B, p, w)
+    return Ppt, plant, cpu, gpu, g2

@@ -6,7 +6,7 @@ import random
 import numpy as np
 import pytest
 from tests import pyec
-from tests.helpers import M64, random_point, giant, candidate_x, synthetic_keys, norm_hits
+from tests.helpers import M64, random_point, giant, candidate_x, synthetic_keys, norm_hits, build_case
 
 pytestmark = pytest.mark.gpu
 P = pyec.P
@@ -83,21 +83,6 @@ CASES = [
     (64, 20, 100, 60000, 14, 1),       # N = 128000 > one wave of threads: several points per thread
     (128, 2, 8, 5000, 4, 2),           # load 312 per bucket: every probe takes the CSR fallback
 ]
-
-
-def build_case(orc, T, B, p, w, htsz, seed, nplant=24):
-    rnd = random.Random(seed)
-    N = T * B * p
-    Ppt = random_point(rnd)
-    plant = []
-    for i in range(nplant):
-        k = rnd.randrange(N) if i > 3 else (0, N - 1, N // 2, 1 % N)[i]
-        plant.append((1 + (i & 1), k))
-    xs = [candidate_x(Ppt, w, k, c) for c, k in plant]
-    keys = synthetic_keys(w, xs, seed)
-    cpu, gpu = orc.build_ht(keys, htsz)
-    g2 = orc.build_g2(T, B, p, w)
-    return Ppt, plant, cpu, gpu, g2
 
 
 @pytest.mark.parametrize("case", CASES)
