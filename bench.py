@@ -329,7 +329,17 @@ def main():
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--with-dropin", action="store_true", help="reference arm only: also time bsgs-cuda_b200/dropin_test1.cubin in the same harness (extra key, off by default)")
     args = ap.parse_args()
-    line = run_reference(args) if args.impl == "reference" else run_b200(args)
+    # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version
+    # banner under NCCL_DEBUG=VERSION, for one) is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference(args) if args.impl == "reference" else run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
     if line is not None:
         print(json.dumps(line), flush=True)
 
