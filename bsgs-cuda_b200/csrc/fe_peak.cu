@@ -1,0 +1,56 @@
+// fe_peak.cu -- what the field arithmetic of fp.cuh delivers on its own: back-to-back fe_mul / fe_sqr
+// on register operands, no memory traffic, no probe, the kernel's own geometry (3 CTAs x 256 threads
+// per SM at <= 80 registers, 2 independent chains per thread).  One giant step of the search costs
+// 2.5 multiplications + 1 squaring, so
+//     ceiling_steps_per_s = 1 / (2.5 * t_mul + t_sqr)
+// is the speed the giant-step kernel would reach if everything around the multiplications (field
+// additions, loads, the probe, loop control) were free.  Prints one JSON object.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "fp.cuh"
+
+#define ITER 2000
+
+template <int OP>
+__global__ void __launch_bounds__(256, 3) spin(uint32_t* out, uint32_t seed) {
+    uint32_t a[8], b[8], c[8], d[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = seed * 0x9E3779B9u + threadIdx.x * 977u + i * 0x85EBCA6Bu; b[i] = a[i] * 3u + blockIdx.x; c[i] = a[i] ^ 0x5bd1e995u; d[i] = b[i] + 17u * i; }
+#pragma unroll 1
+    for (int it = 0; it < ITER; it++) {
+        uint32_t r[8], s[8];
+        if (OP == 0) { fp::fe_mul(r, a, b); fp::fe_mul(s, c, d); }      // two independent products per iteration
+        else { fp::fe_sqr(r, a); fp::fe_sqr(s, c); }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { a[i] = r[i]; c[i] = s[i]; }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x ^= a[i] ^ c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+template <int OP>
+static double run(int sms, uint32_t* out) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    spin<OP><<<sms * 3, 256>>>(out, 1); cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0); spin<OP><<<sms * 3, 256>>>(out, 2 + rep); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+    }
+    return (double)sms * 3 * 256 * ITER * 2 / (best * 1e-3);          // operations per second, whole GPU
+}
+
+int main() {
+    cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
+    int sms = pr.multiProcessorCount;
+    uint32_t* out; cudaMalloc(&out, sizeof(uint32_t) * sms * 3 * 256);
+    double mul = run<0>(sms, out), sqr = run<1>(sms, out);
+    double ceil_steps = 1.0 / (2.5 / mul + 1.0 / sqr);
+    printf("{\"gpu\": \"%s\", \"sms\": %d, \"fe_mul_per_s\": %.4g, \"fe_sqr_per_s\": %.4g, \"giant_step_ceiling_per_s\": %.4g, "
+           "\"how\": \"2.5 fe_mul + 1 fe_sqr per giant step, 3 CTAs x 256 threads per SM, registers only\", \"err\": \"%s\"}\n",
+           pr.name, sms, mul, sqr, ceil_steps, cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
