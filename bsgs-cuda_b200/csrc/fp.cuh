@@ -244,16 +244,18 @@ FP_DEV void fe_copy(uint32_t r[8], const uint32_t a[8]) {
 }
 
 // Low 64 bits of the CANONICAL value of (a + u) mod p, a lazy (< 2^256), u canonical (< p).
-// Fast path touches only what the probe needs; the exact general case is taken when the upper
-// limbs are all ones (probability ~2^-160 for uniform values), see the derivation in DESIGN.md.
+// z = (a + u) mod 2^256 with carry k; the value is z + k*(2^32 + 977).  Its low 64 bits are
+// (z mod 2^64) + k*(2^32 + 977) whatever happens above them, so the fast path needs nothing else --
+// provided the value is already canonical and did not wrap again, which is certain when the top limb
+// of z is not all ones (then z + k*C < 2^256 - 2^224 + 2^33 < p).  Otherwise (probability 2^-32) the
+// exact general case runs.
 FP_DEV uint64_t fe_add_low64_canon(const uint32_t a[8], const uint32_t u[8]) {
     uint32_t z[8];
     add_cc(z[0], a[0], u[0]);
 #pragma unroll
     for (int i = 1; i < 8; i++) addc_cc(z[i], a[i], u[i]);
     uint32_t k; addc(k, 0, 0);
-    uint32_t up = z[3] & z[4] & z[5] & z[6] & z[7];
-    if (up == 0xFFFFFFFFu) {                       // exact slow path
+    if (z[7] == 0xFFFFFFFFu) {                     // exact slow path
         uint32_t c0 = (0u - k) & FP_C0;
         add_cc(z[0], z[0], c0); addc_cc(z[1], z[1], k);
 #pragma unroll

@@ -75,6 +75,8 @@ def test_low64_of_canonical_sum(he):
         cases.append((hi | rnd.getrandbits(96), rnd.randrange(P)))                 # exact slow path
         cases.append((rnd.getrandbits(256), P - 1 - rnd.getrandbits(40)))
         cases.append((2**256 - 1 - rnd.getrandbits(34), P - 1 - rnd.getrandbits(34)))
+        cases.append(((0xFFFFFFFF << 224) | rnd.getrandbits(224), rnd.getrandbits(200)))     # top limb of the sum all ones, the others not
+        cases.append((rnd.getrandbits(256), ((0xFFFFFFFF << 224) | rnd.getrandbits(224)) % P))
     cases += [(a, u % P) for a in EDGE for u in EDGE]
     for a, u in cases:
         assert he.he_add_low64_canon(limbs(a), limbs(u)) == ((a + u) % P) & M64, (hex(a), hex(u))
