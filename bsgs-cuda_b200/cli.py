@@ -243,8 +243,11 @@ def main(argv=None, out=sys.stdout) -> int:
             for th in threads:
                 th.start()
             last_log = time.time(); last_steps = 0
-            while any(th.is_alive() for th in threads):
-                time.sleep(0.05)
+            while True:
+                alive = [th for th in threads if th.is_alive()]
+                if not alive:
+                    break
+                alive[0].join(0.05)                                  # returns at once when the worker ends (no polling quantum per target)
                 if time.time() - last_log > 2:                       # status line, 1_9_7File.pb:5119-5141
                     with state["lock"]:
                         st = state["steps"]
