@@ -19,11 +19,15 @@
 //     coalesced 512-byte transaction;
 //   * the CSR table of the reference (offset pair -> binary search: two dependent random reads) is
 //     re-laid out at upload into one 32-byte sector per bucket holding fifteen 16-bit fingerprints
-//     (top half of the 32-bit tag) and a count.  A probe is ONE 256-bit load (LDG.E.256); only a
-//     fingerprint match (2^-16 per entry) or an over-full bucket (> 15 entries, ~1e-5 at load 4)
-//     consults the CSR image kept beside it, so the emitted records are exactly the reference's;
+//     (from the top half of the 32-bit tag, see fpr16) and a count.  A probe is ONE 256-bit load
+//     (LDG.E.256) and eight fp16x2 compares; only a fingerprint match (~2^-14 per entry) or an
+//     over-full bucket (> 15 entries, ~1e-5 at load 4) consults the CSR image kept beside it, so
+//     the emitted records are exactly the reference's;
 //   * probe keys are parked in a per-thread ring in shared memory and resolved in bursts of four
-//     independent sector loads, so no probe state is live across the arithmetic.
+//     independent sector loads, so no probe state is live across the arithmetic;
+//   * everything rare (padding rows, a tangent Px == Qx, the ragged last burst, a fingerprint
+//     match) goes through one out-of-line exact routine behind a warp vote, so that the hot loop
+//     carries no per-slot bookkeeping.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
