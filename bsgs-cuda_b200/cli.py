@@ -22,6 +22,7 @@ import threading
 import time
 import numpy as np
 from . import ec, formats
+from . import native
 from .native import Engine
 from .search import Search
 
@@ -114,17 +115,17 @@ def load_or_build_tables(o, engines, log):
     if have(f_cpu, formats.htcpu_bytes(w, htsz)) and have(f_gpu, formats.htgpu_bytes(w, htsz)):
         log(f"Load hashtable from {f_gpu}")
         htcpu = formats.load(f_cpu)
-        for e in engines:
-            e.upload_htcpu(htcpu)                                # tags + payloads: enables device-side verification
+        e0.upload_htcpu(htcpu)                                   # tags + payloads: enables device-side verification
+        if len(engines) > 1:
+            native.bcast_ht(engines)
     else:
         log(f"Generate {w} baby points on GPU#{o['devices'][0]}")
         e0.ht_generate()
         htcpu = e0.ht_export("cpu")
-        htgpu = e0.ht_export("gpu") if (len(engines) > 1 or not o["nosave"]) else None
         if not o["nosave"]:
-            formats.save(f_cpu, htcpu); formats.save(f_gpu, htgpu)
-        for e in engines[1:]:
-            e.upload_htcpu(htcpu)
+            formats.save(f_cpu, htcpu); formats.save(f_gpu, e0.ht_export("gpu"))
+        if len(engines) > 1:
+            native.bcast_ht(engines)                             # device to device, not 7 uploads from the host
     for e in engines:
         e.set_verify(True)
     if have(f_g2, formats.g2_bytes(T, B, p)):

@@ -289,6 +289,39 @@ extern "C" int bsgs_upload_ht(bsgs_ctx* ctx, const void* htgpu, size_t bytes) {
     return bsgs_ht_commit(ctx);
 }
 
+extern "C" int bsgs_bcast_ht(bsgs_ctx* const* ctxs, int n) {
+    if (!ctxs || n < 1 || !ctxs[0]) return BSGS_E_ARG;
+    bsgs_ctx* src = ctxs[0];
+    if (!src->ht_ready) return BSGS_E_STATE;
+    const size_t img = ht_image_bytes(src), js = (size_t)src->w * 4;
+    for (int i = 1; i < n; i++)
+        if (!ctxs[i] || ctxs[i] == src || ctxs[i]->w != src->w || ctxs[i]->htsz != src->htsz) return BSGS_E_ARG;
+    // phase 1: allocate, enable peer access where the devices differ, start every copy
+    for (int i = 1; i < n; i++) {
+        bsgs_ctx* ctx = ctxs[i];                                   // (CU() records errors in `ctx`)
+        void* d; size_t nb; int rc = bsgs_ht_staging(ctx, &d, &nb);
+        if (rc) return rc;
+        if (src->d_js && !ctx->d_js) CU(cudaMalloc(&ctx->d_js, js + 16));
+        if (!src->d_js && ctx->d_js) { cudaFree(ctx->d_js); ctx->d_js = nullptr; }
+        if (ctx->dev != src->dev) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, ctx->dev, src->dev));
+            if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(src->dev, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e); cudaGetLastError(); }
+        }
+        CU(cudaMemcpyPeerAsync(d, ctx->dev, src->d_ht, src->dev, img, ctx->stream));      // staged through the host when peers cannot map each other
+        if (src->d_js) CU(cudaMemcpyPeerAsync(ctx->d_js, ctx->dev, src->d_js, src->dev, js, ctx->stream));
+    }
+    // phase 2: wait and build the fingerprint sectors on every destination
+    for (int i = 1; i < n; i++) {
+        bsgs_ctx* ctx = ctxs[i];
+        CU(cudaSetDevice(ctx->dev));
+        CU(cudaStreamSynchronize(ctx->stream));
+        int rc = bsgs_ht_commit(ctx);
+        if (rc) return rc;
+    }
+    return BSGS_OK;
+}
+
 // htCPU file image (4H + 4 + 8w bytes): the same table with the payloads j, which device-side
 // verification needs.  Replaces bsgs_upload_ht for hosts that loaded <...>_htCPUv0.BIN.
 extern "C" int bsgs_upload_htcpu(bsgs_ctx* ctx, const void* htcpu, size_t bytes) {

@@ -37,7 +37,7 @@ class DevInfo(C.Structure):
 EXPORTS = ["bsgs_create", "bsgs_destroy", "bsgs_strerror", "bsgs_last_cuda_error", "bsgs_upload_giants", "bsgs_upload_ht", "bsgs_upload_htcpu",
            "bsgs_giants_staging", "bsgs_giants_commit", "bsgs_ht_staging", "bsgs_ht_commit", "bsgs_step", "bsgs_step_multi",
            "bsgs_giants_generate", "bsgs_giants_export", "bsgs_ht_build_from_keys", "bsgs_ht_generate", "bsgs_ht_build_synthetic", "bsgs_ht_export", "bsgs_ht_device_image",
-           "bsgs_run", "bsgs_time_launches", "bsgs_probe_bench", "bsgs_probe_keys", "bsgs_get_info", "bsgs_set_option", "bsgs_debug_field", "bsgs_device_count", "bsgs_device_query"]
+           "bsgs_run", "bsgs_time_launches", "bsgs_probe_bench", "bsgs_probe_keys", "bsgs_get_info", "bsgs_set_option", "bsgs_debug_field", "bsgs_device_count", "bsgs_device_query", "bsgs_bcast_ht"]
 
 _lib = None
 
@@ -80,6 +80,7 @@ def load():
     L.bsgs_get_info.argtypes = [vp, C.POINTER(Info)]
     L.bsgs_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.bsgs_debug_field.argtypes = [C.c_int, C.c_int, vp, vp, vp, u32]
+    L.bsgs_bcast_ht.argtypes = [C.POINTER(vp), C.c_int]
     L.bsgs_device_count.argtypes = [C.POINTER(C.c_int)]
     L.bsgs_device_query.argtypes = [C.c_int, C.POINTER(DevInfo)]
     _lib = L
@@ -103,6 +104,14 @@ def devices():
         out.append({"index": i, "name": d.name.decode(), "cc": (d.cc_major, d.cc_minor), "sm_count": d.sm_count,
                     "free_bytes": d.free_bytes, "total_bytes": d.total_bytes})
     return out
+
+
+def bcast_ht(engines):
+    """Copy the table of engines[0] to the others device to device (bsgs_bcast_ht)."""
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    rc = load().bsgs_bcast_ht(arr, len(engines))
+    if rc:
+        raise BsgsError(rc, "bsgs_bcast_ht")
 
 
 def debug_field(op: int, a, b, device=0):

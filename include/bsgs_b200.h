@@ -81,6 +81,12 @@ int  bsgs_giants_staging(bsgs_ctx *ctx, void **dev_ptr, size_t *bytes);
 int  bsgs_giants_commit(bsgs_ctx *ctx);
 int  bsgs_ht_staging(bsgs_ctx *ctx, void **dev_ptr, size_t *bytes);
 int  bsgs_ht_commit(bsgs_ctx *ctx);
+/* Single-process form of the same start-up step (the reference runs one host thread per GPU in one
+ * process and uploads the table to every GPU from host memory, 1_9_7File.pb:2337-2350, 4776):
+ * copy the table of ctxs[0] -- the htGPU image and, when present, the payloads used by device-side
+ * verification -- to ctxs[1..n-1] device to device (NVLink peer copies, all in flight at once) and
+ * commit it there.  All contexts must have the same w and htsz; ctxs[0] must hold a table. */
+int  bsgs_bcast_ht(bsgs_ctx *const *ctxs, int n);
 
 /* Device-side construction of the same table image (replaces HashTableInsert + sortHashTable32bit +
  * packHTFile/packHTGPUFile, F197:2555-2622, 2771-2820, 3232-3444): counting sort of `nkeys` (= w)

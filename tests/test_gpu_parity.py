@@ -632,3 +632,29 @@ def test_device_listing_and_suggestion(pkg):
     assert any(l.startswith("Try -t ") and "(this build)" in l for l in lines)
     s = tune.tune_b200(devs[0]["free_bytes"], devs[0]["sm_count"])
     assert s["device_mb"] * 1048576 < devs[0]["free_bytes"]
+
+
+def test_bcast_ht_between_contexts(pkg, orc):
+    """bsgs_bcast_ht: the table of context 0 (a device-side build, with payloads) copied device to
+    device into two more contexts; all three then emit the same records, verified ones included."""
+    T, B, p, w, htsz = 32, 4, 8, 1 << 14, 12
+    rnd = random.Random(77)
+    with pkg.Engine(T, B, p, w, htsz) as e0, pkg.Engine(T, B, p, w, htsz) as e1, pkg.Engine(T, B, p, w, htsz) as e2:
+        for e in (e0, e1, e2):
+            e.giants_generate()
+        e0.ht_generate()
+        pkg.native.bcast_ht([e0, e1, e2])
+        assert bytes(e1.ht_export("gpu")) == bytes(e0.ht_export("gpu")) == bytes(e2.ht_export("gpu"))
+        assert bytes(e2.ht_export("cpu")) == bytes(e0.ht_export("cpu"))
+        secret = rnd.randrange(1, 1 << 24)                               # inside the span of one launch: a real hit exists
+        base = pyec.mul(pyec.G, secret + p * w + 1)                   # some base point whose neighbourhood holds baby points
+        pts = [base, random_point(rnd)]
+        for e in (e0, e1, e2):
+            e.set_verify(True)
+        ref = [norm_hits(e0.step(pt)) for pt in pts]
+        assert ref[0]
+        for e in (e1, e2):
+            assert [norm_hits(e.step(pt)) for pt in pts] == ref
+        with pytest.raises(pkg.BsgsError):                             # different table geometry is refused
+            with pkg.Engine(T, B, p, w, htsz + 1) as bad:
+                pkg.native.bcast_ht([e0, bad])
