@@ -121,8 +121,9 @@ def load_or_build_tables(o, engines, log):
     else:
         log(f"Generate {w} baby points on GPU#{o['devices'][0]}")
         e0.ht_generate()
-        htcpu = e0.ht_export("cpu")
+        htcpu = None                                             # records are verified on the device: no host copy needed
         if not o["nosave"]:
+            htcpu = e0.ht_export("cpu")
             formats.save(f_cpu, htcpu); formats.save(f_gpu, e0.ht_export("gpu"))
         if len(engines) > 1:
             native.bcast_ht(engines)                             # device to device, not 7 uploads from the host
@@ -223,7 +224,12 @@ def main(argv=None, out=sys.stdout) -> int:
                     chunk = min(nwin - done, 16)
                     hits, d = e.run(s.window_point(done), s.D, chunk, batch=chunk, stop_after_hits=1)
                     for (code, idx, win), payload in zip(hits, list(e.payloads)):
-                        k = s.check_verified(code, idx, done + win, payload) if payload != 0xFFFFFFFF else s.check_hit(htcpu, code, idx, done + win)
+                        if payload != 0xFFFFFFFF:
+                            k = s.check_verified(code, idx, done + win, payload)
+                        elif htcpu is not None:
+                            k = s.check_hit(htcpu, code, idx, done + win)
+                        else:
+                            raise RuntimeError("unverified record and no htCPU table on the host")
                         if k is not None:
                             with state["lock"]:
                                 state["key"], state["stop"] = k, True
