@@ -44,6 +44,13 @@ __device__ __forceinline__ Fe ld_words(const uint32_t* p, uint32_t TB) {        
     for (int k = 0; k < 8; k++) r.v[7 - k] = __ldg(p + (size_t)k * TB);
     return r;
 }
+// a random 4-byte table read: cached in L1 as usual (the neighbouring word is read next), but only a
+// 64-byte fill from DRAM into L2 instead of the default 128-byte line
+__device__ __forceinline__ uint32_t ld_tbl(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.L2::64B.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ Fe lds_fe(const uint32_t* s) {
     Fe r;
 #pragma unroll
@@ -92,7 +99,7 @@ extern "C" __global__ void __launch_bounds__(kMaxT, 1) _test1(uint32_t* base) {
     const uint32_t* tags = off + _A[26];
     const uint32_t* X = base + 512;
     const uint32_t* Y = X + (size_t)8 * N;
-    uint32_t* CH = base + 512 + (size_t)16 * N;
+    uint4* CH = reinterpret_cast<uint4*>(base + 512 + (size_t)16 * N);      // private scratch: two 128-bit halves per giant, [r][half][g]
 
     if (threadIdx.x == 0) {
         uint32_t px[8], py[8], z[8], r[8];
@@ -110,22 +117,22 @@ extern "C" __global__ void __launch_bounds__(kMaxT, 1) _test1(uint32_t* base) {
     if (T > kMaxT) return;                           // cannot be launched anyway (register file)
 
     // PASS 1 (PTX197:L149-1297): running product of the denominators; the chain block is private
-    // scratch, so limbs are stored least significant first
+    // scratch, so it is laid out as 128-bit vectors (two coalesced 512-byte warp transactions per element)
     Fe acc; acc.v[0] = 1;
 #pragma unroll
     for (int i = 1; i < 8; i++) acc.v[i] = 0;
     const size_t rowstride = (size_t)8 * TB;
     {
         const uint32_t* xp = X + g;
-        uint32_t* cp = CH + g;
+        uint4* cp = CH + g;
 #pragma unroll 1
-        for (uint32_t r = 0; r < p; r++, xp += rowstride, cp += rowstride) {
+        for (uint32_t r = 0; r < p; r++, xp += rowstride, cp += 2 * (size_t)TB) {
             Fe qx = ld_words(xp, TB), d;
             { Fe px = lds_fe(s_c); fp::fe_sub_canon(d.v, px.v, qx.v); }
             if (fp::fe_is_zero_rare(d.v)) d = lds_fe(s_c + 24);
             Fe n; fp::fe_mul(n.v, acc.v, d.v); acc = n;
-#pragma unroll
-            for (int k = 0; k < 8; k++) cp[(size_t)k * TB] = acc.v[k];
+            cp[0] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+            cp[TB] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
         }
     }
     Fe inv; fp::fe_inv(inv.v, acc.v);               // one inversion per thread (PTX197:L1319-26062 uses 504 multiplications)
@@ -134,15 +141,16 @@ extern "C" __global__ void __launch_bounds__(kMaxT, 1) _test1(uint32_t* base) {
     uint64_t* ring = s_ring + threadIdx.x;
     int fill = 0; uint32_t eqmask = 0;
     const uint32_t* xp = X + g + (size_t)(p - 1) * rowstride;
-    const uint32_t* cp = CH + g + (size_t)(p - 1) * rowstride;
+    const uint4* cp = CH + g + (size_t)(p - 1) * 2 * TB;
     const ptrdiff_t yoff = Y - X;
 #pragma unroll 1
     for (int r = (int)p - 1; r >= 0; r--, xp -= rowstride) {
         Fe cprev;
-        cp -= rowstride;
+        cp -= 2 * (size_t)TB;
         if (r > 0) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) cprev.v[k] = __ldcs(cp + (size_t)k * TB);
+            const uint4 c0 = __ldcs(cp), c1 = __ldcs(cp + TB);
+            cprev.v[0] = c0.x; cprev.v[1] = c0.y; cprev.v[2] = c0.z; cprev.v[3] = c0.w;
+            cprev.v[4] = c1.x; cprev.v[5] = c1.y; cprev.v[6] = c1.z; cprev.v[7] = c1.w;
         } else {
             cprev.v[0] = 1;
 #pragma unroll
@@ -187,7 +195,7 @@ extern "C" __global__ void __launch_bounds__(kMaxT, 1) _test1(uint32_t* base) {
                 for (int j = 0; j < 4; j++) {
                     key[j] = ring[(s0 + j) * kMaxT];
                     const uint32_t h = (uint32_t)key[j] & mask;
-                    lo[j] = off[h]; hi[j] = off[h + 1];
+                    lo[j] = ld_tbl(off + h); hi[j] = ld_tbl(off + h + 1);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -197,7 +205,7 @@ extern "C" __global__ void __launch_bounds__(kMaxT, 1) _test1(uint32_t* base) {
                     const uint32_t tag = (uint32_t)(key[j] >> 32);
                     uint32_t a = lo[j], b = hi[j]; bool found = false;
                     while (a < b) {
-                        uint32_t c = a + ((b - a) >> 1), t = tags[c];
+                        uint32_t c = a + ((b - a) >> 1), t = ld_tbl(tags + c);
                         if (tag > t) a = c + 1; else if (tag < t) b = c; else { found = true; break; }
                     }
                     if (found) record(base, plus ? 1u : (eqj ? 4u : 2u), g * p + (uint32_t)(r_first - pair), true);
