@@ -1,0 +1,114 @@
+"""The C++ host program (bsgs-cuda_b200/bsgs_b200, csrc/host_main.cpp): the reference's main program
+restated above the C ABI.  CPU part: command line, validation and the settings fingerprint agree with
+the Python mirror (bsgs-cuda_b200/cli.py) and with the reference's rules; the end-to-end runs are GPU
+tests at the bottom."""
+import hashlib
+import os
+import random
+import subprocess
+import pytest
+import bsgs_cuda_b200 as b
+from tests import pyec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "bsgs-cuda_b200", "bsgs_b200")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    if not os.path.exists(EXE):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "bsgs-cuda_b200"), "bsgs_b200"])
+    return EXE
+
+
+def run(exe, args, cwd=None):
+    r = subprocess.run([exe] + args, capture_output=True, text=True, cwd=cwd, timeout=600)
+    return r.returncode, r.stdout
+
+
+@pytest.mark.parametrize("line", [
+    "-t 32 -b 4 -p 16 -w 22 -htsz 25 -pk 0x8000000000 -pke 0xFFFFFFFFFF",
+    "-t 512 -b 148 -p 256 -w 30 -htsz 28 -pk 0x10000000000000000 -pke 0x1ffffffffffffffff",
+    "-w 30.5 -htsz 29 -pk 80000000000000000000 -pke FFFFFFFFFFFFFFFFFFFF",
+    "-w 31.5 -htsz 29", "-w 4194304", "",
+])
+def test_fingerprint_equals_python_mirror_and_reference_rule(exe, line):
+    rc, out = run(exe, line.split() + ["-fingerprint"])
+    o = b.cli.parse_args(line.split())
+    assert rc == 0 and out.strip().splitlines()[-1] == b.cli.fingerprint(o)
+    # the rule itself (1_9_7File.pb:4634-4636): SHA-1 of Str(T)+Str(B)+Str(p)+Str(w)+pk+pke+Str(htsz)
+    s = f"{o['t']}{o['b']}{o['p']}{o['w']}{o['pk_str']}{o['pke_str']}{o['htsz']}"
+    assert out.strip().splitlines()[-1] == hashlib.sha1(s.encode()).hexdigest()
+
+
+@pytest.mark.parametrize("bad,msg", [("-zz", "Unknown parameter"), ("-p 7", "multiple of 2"), ("-htsz 32", "less or equal to 31"),
+                                     ("-w 3069485951", "less than 3069485951"), ("-pk 0", "more than 0"), ("-pk 0x10 -pke 0x10", "more than range begin"),
+                                     ("-infile /nonexistent/pubs.txt", "not found")])
+def test_usage_errors_match_the_python_mirror(exe, bad, msg):
+    rc, out = run(exe, bad.split() + ["-fingerprint"])
+    assert rc == 2 and msg in out
+    with pytest.raises(b.cli.UsageError):
+        b.cli.validate(b.cli.parse_args(bad.split())); b.cli.read_pubs(b.cli.parse_args(bad.split()))
+
+
+def test_unsafe_warning(exe):
+    rc, out = run(exe, "-htsz 28 -w 1777178604 -fingerprint".split())
+    assert rc == 0 and "UNSAFE" in out                                                  # README.md:19-24 of the reference
+
+
+# ------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_cpp_host_config0_puzzle40_and_table_files(exe, tmp_path):
+    """BASELINE.json configs[0] through the C++ host: key, win.txt, the reference's file names and
+    sizes; the files it writes are byte-identical to the ones the Python mirror writes; a second run
+    loads them instead of generating."""
+    args = "-t 32 -b 4 -p 16 -w 22 -htsz 25 -pk 0x8000000000 -pke 0xffffffffff -pb 03a2efa402fd5268400c77c20e574ba86409ededee7c4020e4b9f0edbee53de0d4".split()
+    d1 = tmp_path / "cpp"; d1.mkdir()
+    rc, out = run(exe, args, cwd=d1)
+    key = "KEY[1]: 0x" + format(0xE9AE4933D6, "064x")
+    assert rc == 0 and key in out and "Generate 4194304 baby points" in out and "finished, found 1 of 1" in out
+    assert open(d1 / "win.txt").read().startswith(key)
+    names = {b.formats.htcpu_name(4194304, 25): 167772164, b.formats.htgpu_name(4194304, 25): 150994948, "32_4_16_4194304_g2.BIN": 32 * 4 * 16 * 64}
+    for n, size in names.items():
+        assert os.path.getsize(d1 / n) == size
+    rc, out = run(exe, args, cwd=d1)
+    assert rc == 0 and "Load hashtable" in out and "Load giants" in out and key in out
+    # the Python mirror writes the same bytes
+    import io
+    d2 = tmp_path / "py"; d2.mkdir()
+    cwd = os.getcwd(); os.chdir(d2)
+    try:
+        assert b.cli.main(args, out=io.StringIO()) == 0
+    finally:
+        os.chdir(cwd)
+    for n in names:
+        assert hashlib.sha256(open(d1 / n, "rb").read()).digest() == hashlib.sha256(open(d2 / n, "rb").read()).digest()
+
+
+@pytest.mark.gpu
+def test_cpp_host_infile_and_resume(exe, tmp_path):
+    """-infile with several targets over a 256-bit range start (tables built once), then -wl resume
+    from a checkpoint written in the reference's format (1_9_7File.pb:3913-3921)."""
+    rnd = random.Random(20261017)
+    pk = 0x49dccfd96dc5df56487436f5a1b18c4f5d34f65ddb48cb5e0000000000000000
+    secrets = [pk + rnd.randrange(1, 1 << 36) for _ in range(4)]
+    pts = [pyec.mul(pyec.G, s) for s in secrets]
+    with open(tmp_path / "pubs.txt", "w") as f:
+        for i, pt in enumerate(pts):
+            f.write((b.ec.compress(pt) if i % 2 else format(pt[0], "064x") + format(pt[1], "064x")) + "\n")
+    common = f"-t 32 -b 4 -p 16 -w 18 -htsz 16 -pk {pk:x} -pke {pk + (1 << 36):x} -infile pubs.txt -nosave"
+    rc, out = run(exe, common.split(), cwd=tmp_path)
+    assert rc == 0 and "found 4 of 4" in out and out.count("Generate") == 2
+    for i, s in enumerate(secrets, start=1):
+        assert f"KEY[{i}]: 0x{s:064x}" in out
+    # resume: position 3, counter of a window before the one that holds key 3
+    o = b.cli.parse_args(common.split())
+    srch = b.Search(32, 4, 16, 1 << 18, 16, pk, pts[2])
+    jwin = next(j for j in range(srch.windows_needed(pk + (1 << 36))) if abs((secrets[2] - pk) - (srch.window_key(j) + srch.centerbig)) <= srch.stride // 2 + (1 << 18))
+    cnt = srch.window_key(max(jwin - 1, 0))
+    b.cli.save_checkpoint(3, format(pts[2][0], "064x") + format(pts[2][1], "064x"), cnt, b.cli.fingerprint(o), path=str(tmp_path / "currentwork.txt"))
+    rc, out = run(exe, (common + " -wl currentwork.txt").split(), cwd=tmp_path)
+    assert rc == 0 and f"KEY[3]: 0x{secrets[2]:064x}" in out and "KEY[1]" not in out and "KEY[2]" not in out and f"KEY[4]: 0x{secrets[3]:064x}" in out
+    # a checkpoint of another configuration is refused (1_9_7File.pb:4668-4672)
+    rc, out = run(exe, (common.replace("-p 16", "-p 18") + " -wl currentwork.txt").split(), cwd=tmp_path)
+    assert rc == 2 and "different" in out
