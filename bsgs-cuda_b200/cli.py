@@ -41,7 +41,7 @@ def cut_hex(s: str) -> str:                                          # cutHex, 1
 
 def parse_args(argv):
     o = dict(DEFAULTS)
-    o.update(infile=None, wl=None, sf=1, pb_given=False, pk_str="01", pke_str="1ffffffffffffffff", nosave=False)
+    o.update(infile=None, wl=None, sf=1, pb_given=False, pk_str="01", pke_str="1ffffffffffffffff", nosave=False, onlygen=False)
     i = 0
     takes = {"-t": ("t", int), "-b": ("b", int), "-p": ("p", int), "-d": ("d", str), "-htsz": ("htsz", int), "-infile": ("infile", str),
              "-wl": ("wl", str), "-sf": ("sf", int)}
@@ -52,6 +52,8 @@ def parse_args(argv):
             raise UsageError(__doc__)
         if a == "-nosave":                                           # extension: keep the generated tables in HBM/RAM only
             o["nosave"] = True; i += 1; continue
+        if a == "-onlygen":                                          # the role of onlygen1_9_6File.pb: write the table files and stop
+            o["onlygen"] = True; i += 1; continue
         if a in takes:
             if val is not None:
                 o[takes[a][0]] = takes[a][1](val); i += 1
@@ -84,6 +86,8 @@ def validate(o):
         raise UsageError("-htsz should be less or equal to 31")
     if o["p"] % 2:
         raise UsageError("vaule -p must be a multiple of 2")
+    if o.get("onlygen") and (o["t"] % 2 or o["b"] % 2):
+        raise UsageError("vaule -t and -b must be a multiple of 2")   # onlygen1_9_6File.pb:3140-3145
     if o["pk"] == 0:
         raise UsageError("Range begin should be more than 0")
     if o["pke"] <= o["pk"]:
@@ -199,6 +203,11 @@ def main(argv=None, out=sys.stdout) -> int:
     engines = [Engine(T, B, p, w, htsz, device=d) for d in o["devices"]]
     R = len(engines)
     try:
+        if o["onlygen"]:                                             # onlygen1_9_6File.pb:3182-3205
+            o["nosave"] = False
+            load_or_build_tables(o, engines, log)
+            log("finished ok")
+            return 0
         htcpu = load_or_build_tables(o, engines, log)
         found_total = 0
         for listpos, pub in enumerate(pubs, start=1):

@@ -139,7 +139,7 @@ struct Options {
     uint32_t t = 256, b = 132, p = 400, htsz = 25; uint64_t w = 1ull << 25; int wt = 180, sf = 1;    // 1_9_7File.pb:181-186, 168, 152
     std::string pb = "036d05521c67b9cc1c0ef906b42215c7120c7302c34d9316a2726199bedac50936", d = "0", infile, wl;
     std::string pk_str = "01", pke_str = "1ffffffffffffffff";
-    U256 pk = from_u64(1), pke; bool nosave = false, fingerprint_only = false;
+    U256 pk = from_u64(1), pke; bool nosave = false, fingerprint_only = false, onlygen = false;
     std::vector<int> devices;
 };
 struct UsageError { std::string msg; };
@@ -156,6 +156,7 @@ Options parse_args(const std::vector<std::string>& argv) {
         const std::string val = has ? argv[i + 1] : "";
         if (a == "-h") throw UsageError{"usage: bsgs_b200 -t T -b B -p P -w W -htsz H -pb PUB -pk HEX -pke HEX [-d 0,1] [-infile F] [-wl F] [-wt S] [-nosave]"};
         if (a == "-nosave") { o.nosave = true; continue; }
+        if (a == "-onlygen") { o.onlygen = true; continue; }                 // the role of onlygen1_9_6File.pb: write the table files and stop
         if (a == "-fingerprint") { o.fingerprint_only = true; continue; }    // extension used by the tests: print the settings hash and exit
         if (a == "-t") { if (has) { o.t = (uint32_t)atoi(val.c_str()); i++; } }
         else if (a == "-b") { if (has) { o.b = (uint32_t)atoi(val.c_str()); i++; } }
@@ -180,6 +181,7 @@ std::vector<std::string> validate(const Options& o) {                    // 1_9_
     if (o.w >= 3069485951ull) throw UsageError{"-w should be less than 3069485951"};
     if (o.htsz > 31) throw UsageError{"-htsz should be less or equal to 31"};
     if (o.p % 2) throw UsageError{"vaule -p must be a multiple of 2"};
+    if (o.onlygen && (o.t % 2 || o.b % 2)) throw UsageError{"vaule -t and -b must be a multiple of 2"};      // onlygen1_9_6File.pb:3140-3145
     if (is_zero(o.pk)) throw UsageError{"Range begin should be more than 0"};
     if (cmp(o.pke, o.pk) <= 0) throw UsageError{"Range end should be more than range begin"};
     std::vector<std::string> warn;
@@ -415,7 +417,13 @@ int run(const std::vector<std::string>& argv) {
     std::vector<bsgs_ctx*> ctx(o.devices.size(), nullptr);
     for (size_t i = 0; i < ctx.size(); i++) ck(bsgs_create(&ctx[i], o.devices[i], o.t, o.b, o.p, o.w, o.htsz), "bsgs_create");
     const int R = (int)ctx.size();
+    if (o.onlygen) o.nosave = false;
     load_or_build_tables(o, ctx);
+    if (o.onlygen) {                                                       // onlygen1_9_6File.pb:3182-3205
+        for (auto c : ctx) bsgs_destroy(c);
+        logln("finished ok");
+        return 0;
+    }
     int found_total = 0, rc = 0;
     for (size_t li = 0; li < pubs.size() && rc == 0; li++) {
         const int listpos = (int)li + 1;

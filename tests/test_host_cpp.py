@@ -112,3 +112,33 @@ def test_cpp_host_infile_and_resume(exe, tmp_path):
     # a checkpoint of another configuration is refused (1_9_7File.pb:4668-4672)
     rc, out = run(exe, (common.replace("-p 16", "-p 18") + " -wl currentwork.txt").split(), cwd=tmp_path)
     assert rc == 2 and "different" in out
+
+
+@pytest.mark.gpu
+def test_onlygen_writes_the_reference_files(exe, tmp_path):
+    """-onlygen = the role of onlygen1_9_6File.pb: the three table files, then "finished ok"; both hosts
+    write the same bytes, and the files pass the reference's own validators restated in the oracle."""
+    import io
+    args = "-t 32 -b 4 -p 16 -w 16 -htsz 12 -onlygen".split()
+    d1 = tmp_path / "cpp"; d1.mkdir()
+    rc, out = run(exe, args, cwd=d1)
+    assert rc == 0 and out.strip().endswith("finished ok") and "KEY" not in out
+    d2 = tmp_path / "py"; d2.mkdir()
+    cwd = os.getcwd(); os.chdir(d2)
+    try:
+        buf = io.StringIO()
+        assert b.cli.main(args, out=buf) == 0 and buf.getvalue().strip().endswith("finished ok")
+    finally:
+        os.chdir(cwd)
+    w, htsz = 1 << 16, 12
+    for n, size in ((b.formats.htcpu_name(w, htsz), b.formats.htcpu_bytes(w, htsz)), (b.formats.htgpu_name(w, htsz), b.formats.htgpu_bytes(w, htsz)), ("32_4_16_65536_g2.BIN", 32 * 4 * 16 * 64)):
+        a1, a2 = open(d1 / n, "rb").read(), open(d2 / n, "rb").read()
+        assert len(a1) == size and a1 == a2
+    from oracle import oracle as orc
+    orc.build(); orc.lib()
+    import numpy as np
+    assert bytes(orc.build_g2(32, 4, 16, w)) == open(d1 / "32_4_16_65536_g2.BIN", "rb").read()
+    cpu, gpu = orc.build_ht(orc.baby_keys(w), htsz)
+    assert bytes(cpu) == open(d1 / b.formats.htcpu_name(w, htsz), "rb").read() and bytes(gpu) == open(d1 / b.formats.htgpu_name(w, htsz), "rb").read()
+    rc, out = run(exe, "-t 31 -b 4 -p 16 -onlygen -fingerprint".split())
+    assert rc == 2 and "multiple of 2" in out
