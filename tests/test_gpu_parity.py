@@ -258,6 +258,27 @@ def test_dropin_module_codes_4_5_and_repeat_launches(orc):
         assert first == again == norm_hits(orc.launch(g2, T, B, p, gpu, htsz, Ppt))
 
 
+def test_dropin_module_as_ptx_text_like_the_reference_embeds_it(orc, tmp_path):
+    """The reference hands PTX TEXT to cuModuleLoadData (1_9_7File.pb:2194), de-obfuscated from its
+    DataSection: take dropin_test1.ptx through scripts/make_datasection.py and back, let the driver
+    JIT it, and compare records with the oracle."""
+    import importlib.util
+    ptx = DROPIN[:-len("cubin")] + "ptx"
+    if not (os.path.exists(orc.REF_LIB) and os.path.exists(ptx)):
+        pytest.skip("harness or drop-in PTX not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_datasection", os.path.join(root, "scripts", "make_datasection.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    text = m.decode(m.encode(open(ptx, "rb").read())).rstrip(b"\0")          # what the host holds after its XOR loop
+    path = tmp_path / "embedded.ptx"; path.write_bytes(text)
+    T, B, p, w, htsz = 64, 6, 10, 20000, 11
+    Ppt, plant, cpu, gpu, g2 = build_case(orc, T, B, p, w, htsz, seed=4321)
+    k = orc.RefKernel(T, B, p, w, htsz, cubin=str(path)); k.upload(g2, gpu)
+    got, count, _ = k.launch(Ppt)
+    k.close()
+    assert got == norm_hits(orc.launch(g2, T, B, p, gpu, htsz, Ppt)) and set(plant) <= set(got)
+
+
 def test_dropin_module_record_area_is_bounded(orc):
     """More than 240 hits: the counter keeps counting, the giants just above the record area stay
     intact (the reference overwrites them, 1_9_7File.pb:2337) -- a second launch still agrees."""
