@@ -81,3 +81,21 @@ def test_datasection_writer_round_trip(tmp_path):
     text = m.encode(ptx)
     assert text.startswith("DataSection") and "BSGS4_cuda_quad_htchangeble_v2:" in text
     assert m.decode(text).rstrip(b"\0") == ptx
+
+
+def test_purebasic_binding_lists_only_declared_functions():
+    """include/bsgs_b200.pbi (the binding a PureBasic maintainer includes) names only functions the
+    header declares, the whole reference-facing set among them, and the same status codes."""
+    pbi = open(os.path.join(ROOT, "include", "bsgs_b200.pbi")).read()
+    code = "\n".join(l.split(";")[0] for l in pbi.splitlines())
+    listed = set(re.findall(r"\b(bsgs_[a-z0-9_]+)\s*\(", code))
+    assert listed <= set(declared_functions())
+    for must in ("bsgs_create", "bsgs_destroy", "bsgs_upload_giants", "bsgs_upload_ht", "bsgs_step", "bsgs_step_multi", "bsgs_run",
+                 "bsgs_giants_generate", "bsgs_ht_generate", "bsgs_ht_export", "bsgs_bcast_ht", "bsgs_set_option"):
+        assert must in listed
+    hdr = open(os.path.join(ROOT, "include", "bsgs_b200.h")).read()
+    for name, val in re.findall(r"#(BSGS_[A-Z_]+)\s*=\s*(-?\d+)", code):
+        if name == "BSGS_MAX_WINDOWS":
+            assert re.search(r"#define BSGS_MAX_WINDOWS\s+%s\b" % val, hdr)
+        else:
+            assert re.search(r"\b%s\s*=\s*%s\b" % (name, val), hdr), name
