@@ -199,9 +199,9 @@ __device__ __noinline__ uint64_t double_x_low64_v(Fe px, Fe inv2y) { return doub
 // index cj = ci_first - slot/2 (row cj / W, window cj % W) -- whether the row is padding (giant index
 // >= N), whether the pair was a tangent (Px == Qx: slot 2j holds X(2P), code 4, and slot 2j+1 is
 // stale), whether the slot lies beyond the ragged last burst -- then the exact CSR lookup alone decides
-// (the fingerprint sector is only a filter in front of it)
-// (PTX197:L33723-34006).  Reached for a fingerprint match (2^-16 per table entry), an over-full
-// bucket, or when the burst contained any of the rare cases above.
+// (PTX197:L33723-34006; the fingerprint sector is only a filter in front of it).  Reached for a
+// fingerprint match (~2^-14 per table entry), an over-full bucket, or when the burst contained any
+// of the rare cases above.
 static __device__ __noinline__ void drain_slow(const Tables& tb, const uint32_t* s_win, int W, uint32_t t, int ci_first, int slot, int fill, uint64_t key) {
     if (slot >= fill) return;
     const int cj = ci_first - (slot >> 1), rj = cj / W, wj = cj - rj * W;
@@ -280,7 +280,7 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
     // pointer into the chain, the window-constant pointer (which doubles as the window counter) and
     // the ring fill.  The rare cases -- a padding row (giant index >= N), a
     // tangent (Px == Qx) or the ragged last burst -- only raise `special`; the drain then classifies
-    // every slot from its chain index (classify_slot) instead of the loop tracking per-slot masks.
+    // every slot from its chain index (drain_slow) instead of the loop tracking per-slot masks.
     int fill = 0;
     bool special = false;
     uint32_t kidx = (uint32_t)(PP - 1) * NT + t;                    // giant index of the current row
