@@ -9,7 +9,7 @@
 #define CH 8
 __constant__ uint32_t cb[64];
 
-// KIND: 0 IADD3, 1 SHF (funnel shift), 2 IMAD.LO, 3 SETP+SEL; KIND2 additionally 4 FFMA, 5 DFMA, 6 HSET2 (fp16x2 compare)
+// KIND: 0 IADD3, 1 SHF (funnel shift), 2 IMAD.LO, 3 SETP+SEL, 8 LOP3 with 3 register reads; KIND2 additionally 4 FFMA, 5 DFMA, 6 HSET2 (fp16x2 compare)
 template <int NW, int NB, int KIND, int NB2 = 0, int KIND2 = 0>
 __global__ void __launch_bounds__(1024, 1) mix(uint64_t* out, uint32_t seed, long long* cycles) {
     uint64_t acc[CH]; uint32_t x[CH], y[CH], mm[CH]; float f[CH]; double df[CH];
@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(1024, 1) mix(uint64_t* out, uint32_t seed, lon
                 if (KIND == 1) asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(x[i]) : "r"(mm[(i + 1) % CH]));
                 if (KIND == 2) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x[i]) : "r"(mm[(i + 1) % CH]), "r"(b));
                 if (KIND == 3) asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; selp.u32 %0, %0, %1, p; }" : "+r"(x[i]) : "r"(mm[(i + 1) % CH]), "r"(b));
+                if (KIND == 8) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(mm[(i + 1) % CH]), "r"(mm[(i + 2) % CH]));   // three register reads
             }
 #pragma unroll
             for (int k = 0; k < NB2; k++) {
@@ -96,6 +97,9 @@ int main() {
     run<1, 0, 0, 1, 4>("wide1_ffma_1", sms, out, cyc, false);
     run<1, 0, 0, 2, 4>("wide1_ffma_2", sms, out, cyc, false);
     run<2, 3, 0>("wide2_iadd3_3", sms, out, cyc, false);
+    run<1, 1, 8>("wide1_lop3r_1", sms, out, cyc, false);
+    run<1, 2, 8>("wide1_lop3r_2", sms, out, cyc, false);
+    run<1, 3, 8>("wide1_lop3r_3", sms, out, cyc, false);
     run<0, 0, 0, 1, 5>("dfma_1", sms, out, cyc, false);
     run<1, 0, 0, 1, 5>("wide1_dfma_1", sms, out, cyc, false);
     run<1, 0, 0, 2, 5>("wide1_dfma_2", sms, out, cyc, false);
