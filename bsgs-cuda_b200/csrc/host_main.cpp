@@ -143,6 +143,7 @@ struct Options {
     std::vector<int> devices;
 };
 struct UsageError { std::string msg; };
+void print_try(unsigned long long free_bytes, int sm, int major, int minor);      // Tune listing, below
 
 uint64_t parse_w(const std::string& arg) {                                // 1_9_7File.pb:1013-1021: <= 32 means Int(2^x)
     double v = atof(arg.c_str());
@@ -158,6 +159,11 @@ Options parse_args(const std::vector<std::string>& argv) {
         if (a == "-nosave") { o.nosave = true; continue; }
         if (a == "-onlygen") { o.onlygen = true; continue; }                 // the role of onlygen1_9_6File.pb: write the table files and stop
         if (a == "-fingerprint") { o.fingerprint_only = true; continue; }    // extension used by the tests: print the settings hash and exit
+        if (a == "-tune") {                                                  // extension used by the tests: -tune free_bytes,sm,major,minor prints the Try lines
+            unsigned long long mem = 0; int sm = 0, mj = 0, mn = 0;
+            if (!has || sscanf(val.c_str(), "%llu,%d,%d,%d", &mem, &sm, &mj, &mn) != 4) throw UsageError{"-tune free_bytes,sm,major,minor"};
+            print_try(mem, sm, mj, mn); exit(0);
+        }
         if (a == "-t") { if (has) { o.t = (uint32_t)atoi(val.c_str()); i++; } }
         else if (a == "-b") { if (has) { o.b = (uint32_t)atoi(val.c_str()); i++; } }
         else if (a == "-p") { if (has) { o.p = (uint32_t)atoi(val.c_str()); i++; } }
@@ -247,6 +253,20 @@ bool tune_b200(unsigned long long free_bytes, int sm, double& wexp, long long& p
     return false;
 }
 void logln(const std::string& s) { printf("%s\n", s.c_str()); fflush(stdout); }
+void print_try(unsigned long long free_bytes, int sm, int major, int minor) {
+    char buf[512];
+    int cores = cores_for(major, minor, sm);
+    snprintf(buf, sizeof buf, "Device have: MP:%d Cores+%d", sm, cores); logln(buf);
+    if (!sm || !cores) return;
+    Try r = tune_reference((long long)free_bytes, sm, cores);
+    if (r.ok) { snprintf(buf, sizeof buf, "Try -t %lld -b %lld -p %lld -w %lld -htsz %lld [%.3f MB]   (reference Tune)", r.t, r.b, r.p, r.k, r.htsz, r.mb); logln(buf); }
+    double we, mb; long long p; int hs;
+    if (tune_b200(free_bytes, sm, we, p, hs, mb)) {
+        if (we == floor(we)) snprintf(buf, sizeof buf, "Try -t 512 -b %d -p %lld -w %d -htsz %d [%.3f MB]   (this build)", sm, p, (int)we, hs, mb);
+        else snprintf(buf, sizeof buf, "Try -t 512 -b %d -p %lld -w %.1f -htsz %d [%.3f MB]   (this build)", sm, p, we, hs, mb);
+        logln(buf);
+    }
+}
 void list_devices() {
     int n = 0;
     if (bsgs_device_count(&n) != BSGS_OK) { logln("device listing unavailable"); return; }
@@ -255,18 +275,7 @@ void list_devices() {
         if (bsgs_device_query(i, &d) != BSGS_OK) continue;
         char buf[512];
         snprintf(buf, sizeof buf, "Cuda device:%s (%.3f/%lluMB)", d.name, (double)d.free_bytes / 1048576.0, (unsigned long long)(d.total_bytes / 1048576)); logln(buf);
-        int cores = cores_for(d.cc_major, d.cc_minor, d.sm_count);
-        snprintf(buf, sizeof buf, "Device have: MP:%d Cores+%d", d.sm_count, cores); logln(buf);
-        if (d.sm_count && cores) {
-            Try r = tune_reference((long long)d.free_bytes, d.sm_count, cores);
-            if (r.ok) { snprintf(buf, sizeof buf, "Try -t %lld -b %lld -p %lld -w %lld -htsz %lld [%.3f MB]   (reference Tune)", r.t, r.b, r.p, r.k, r.htsz, r.mb); logln(buf); }
-            double we, mb; long long p; int hs;
-            if (tune_b200(d.free_bytes, d.sm_count, we, p, hs, mb)) {
-                if (we == floor(we)) snprintf(buf, sizeof buf, "Try -t 512 -b %d -p %lld -w %d -htsz %d [%.3f MB]   (this build)", d.sm_count, p, (int)we, hs, mb);
-                else snprintf(buf, sizeof buf, "Try -t 512 -b %d -p %lld -w %.1f -htsz %d [%.3f MB]   (this build)", d.sm_count, p, we, hs, mb);
-                logln(buf);
-            }
-        }
+        print_try(d.free_bytes, d.sm_count, d.cc_major, d.cc_minor);
         logln("---------------");
     }
 }

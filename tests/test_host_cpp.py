@@ -142,3 +142,22 @@ def test_onlygen_writes_the_reference_files(exe, tmp_path):
     assert bytes(cpu) == open(d1 / b.formats.htcpu_name(w, htsz), "rb").read() and bytes(gpu) == open(d1 / b.formats.htgpu_name(w, htsz), "rb").read()
     rc, out = run(exe, "-t 31 -b 4 -p 16 -onlygen -fingerprint".split())
     assert rc == 2 and "multiple of 2" in out
+
+
+@pytest.mark.parametrize("mem,sm,major,minor", [(178_000_000_000, 148, 10, 0), (10_500_000_000, 68, 7, 5), (80_000_000_000, 132, 9, 0),
+                                                (24_000_000_000, 82, 8, 6), (1_000_000_000, 6, 8, 6), (6_000_000_000, 20, 6, 1)])
+def test_tune_lines_equal_the_python_mirror(exe, mem, sm, major, minor):
+    """Both hosts print the same `Try ...` suggestions (Tune, 1_9_7File.pb:324-431 restated, and this build's own)."""
+    from bsgs_cuda_b200 import tune
+    rc, out = run(exe, ["-tune", f"{mem},{sm},{major},{minor}"])
+    lines = out.strip().splitlines()
+    cores = tune.cores_for(major, minor, sm)
+    assert rc == 0 and lines[0] == f"Device have: MP:{sm} Cores+{cores}"
+    want = []
+    r = tune.tune_reference(mem, sm, cores)
+    if r:
+        want.append(tune.format_try(r).split(" Gen RAM")[0] + "   (reference Tune)")
+    o = tune.tune_b200(mem, sm)
+    if o:
+        want.append(tune.format_try(o) + "   (this build)")
+    assert lines[1:] == want
