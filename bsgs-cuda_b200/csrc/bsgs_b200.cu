@@ -613,10 +613,14 @@ extern "C" int bsgs_probe_bench(bsgs_ctx* ctx, uint64_t nkeys, uint64_t seed, ui
     CU(cudaSetDevice(ctx->dev));
     gs::Tables tb = make_tables(ctx);
     CU(cudaMemsetAsync(ctx->d_scratch, 0, 8, ctx->stream));
-    uint32_t grid = (uint32_t)ctx->sm_count * 8;
+    const char* env_u = getenv("BSGS_PROBE_UNROLL"); const char* env_g = getenv("BSGS_PROBE_CTAS");   // measurement knobs
+    const int unroll = env_u ? atoi(env_u) : 8;
+    uint32_t grid = (uint32_t)ctx->sm_count * (env_g ? (uint32_t)atoi(env_g) : 16u);
     CU(cudaEventRecord(ctx->e0, ctx->stream));
     for (uint32_t i = 0; i < iters; i++) {
-        gs::k_probe_bench_fp<<<grid, 256, 0, ctx->stream>>>(tb, nkeys, seed + i * nkeys, ctx->d_scratch);
+        if (unroll >= 8) gs::k_probe_bench_fp<8><<<grid, 256, 0, ctx->stream>>>(tb, nkeys, seed + i * nkeys, ctx->d_scratch);
+        else if (unroll <= 2) gs::k_probe_bench_fp<2><<<grid, 256, 0, ctx->stream>>>(tb, nkeys, seed + i * nkeys, ctx->d_scratch);
+        else gs::k_probe_bench_fp<4><<<grid, 256, 0, ctx->stream>>>(tb, nkeys, seed + i * nkeys, ctx->d_scratch);
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->e1, ctx->stream));

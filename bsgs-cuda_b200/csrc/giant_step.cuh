@@ -373,15 +373,16 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
 }
 
 // probe-only kernels on the fingerprint layout (measurement + parity of the table layout)
+template <int U>
 __global__ void __launch_bounds__(256) k_probe_bench_fp(const Tables tb, uint64_t nkeys, uint64_t seed, unsigned long long* nfound) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
     unsigned long long found = 0;
-    for (; i < nkeys; i += 4 * stride) {                            // 4 independent sector reads in flight per thread
-        FpSector q[4]; uint64_t k[4]; bool v[4];
+    for (; i < nkeys; i += U * stride) {                            // U independent sector reads in flight per thread
+        FpSector q[U]; uint64_t k[U]; bool v[U];
 #pragma unroll
-        for (int j = 0; j < 4; j++) { v[j] = i + j * stride < nkeys; k[j] = splitmix64(seed + i + j * stride); if (v[j]) q[j].load(tb, (uint32_t)k[j] & tb.mask); }
+        for (int j = 0; j < U; j++) { v[j] = i + j * stride < nkeys; k[j] = splitmix64(seed + i + j * stride); if (v[j]) q[j].load(tb, (uint32_t)k[j] & tb.mask); }
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+        for (int j = 0; j < U; j++)
             if (v[j] && q[j].maybe((uint32_t)(k[j] >> 32)) && probe_csr(tb.csr_off, tb.csr_tags, (uint32_t)k[j] & tb.mask, (uint32_t)(k[j] >> 32))) found++;
     }
     if (found) atomicAdd(nfound, found);
