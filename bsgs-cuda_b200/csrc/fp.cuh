@@ -73,13 +73,16 @@ FP_DEV void subc(uint32_t& r, uint32_t a, uint32_t b) { r = a - b - g_cc; }
 #define FP_P1 0xFFFFFFFEu
 #define FP_C0 977u            // 2^256 mod p = 2^32 + 977
 
-// acc[0..7] (four 64-bit slots) += a[0],a[2],a[4],a[6] * b, carry rippled into acc[8]
-FP_DEV void mad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
+// acc[0..7] (four 64-bit slots) += a[0],a[2],a[4],a[6] * b; the carry out of the top slot is counted in
+// `cw`, a separate word of weight acc[8] -- NOT added into acc[8] itself, so that the top slot of the
+// next row is still untouched when that row reaches it and its product needs no 64-bit addend
+// (an addend (carry, 0) costs a register move on the multiplier pipe for the zero half).
+FP_DEV void mad_row(uint32_t* acc, const uint32_t* a, uint32_t b, uint32_t& cw) {
     madw_cc(acc[0], acc[1], a[0], b);
     madwc_cc(acc[2], acc[3], a[2], b);
     madwc_cc(acc[4], acc[5], a[4], b);
     madwc_cc(acc[6], acc[7], a[6], b);
-    addc(acc[8], acc[8], 0);
+    addc(cw, cw, 0);
 }
 
 // r = v[0..15] mod p (lazy, < 2^256): fold the high half by 2^256 = 2^32 + 977 (mod p) twice.
@@ -132,22 +135,30 @@ FP_DEV void reduce512(uint32_t r[8], uint32_t v[16]) {
 
 // r = a*b mod p (lazy in, lazy out).  64 + 9 multiplier issues.
 FP_DEV void fe_mul(uint32_t r[8], const uint32_t a[8], const uint32_t b[8]) {
-    uint32_t e[18], o[18];                         // e[k]: limb k ; o[k]: limb k+1
+    uint32_t e[16], o[16];                         // e[k]: limb k ; o[k]: limb k+1
+    uint32_t cw[9];                                // row carries: cw[k] has the weight of limb 8 + k (cw[8]: limb 16, always 0)
 #pragma unroll
-    for (int i = 0; i < 18; i++) { e[i] = 0; o[i] = 0; }
+    for (int i = 0; i < 16; i++) { e[i] = 0; o[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 9; i++) cw[i] = 0;
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
-        mad_row(e + i, a, b[i]);                   // a_even * b_even  -> even columns
-        mad_row(o + i, a + 1, b[i]);               // a_odd  * b_even  -> odd columns
-        mad_row(o + i, a, b[i + 1]);               // a_even * b_odd   -> odd columns
-        mad_row(e + i + 2, a + 1, b[i + 1]);       // a_odd  * b_odd   -> even columns
+        mad_row(e + i, a, b[i], cw[i]);                    // a_even * b_even  -> even columns, carry at limb i + 8
+        mad_row(o + i, a + 1, b[i], cw[i + 1]);            // a_odd  * b_even  -> odd columns,  carry at limb i + 9
+        mad_row(o + i, a, b[i + 1], cw[i + 1]);            // a_even * b_odd   -> odd columns,  carry at limb i + 9
+        mad_row(e + i + 2, a + 1, b[i + 1], cw[i + 2]);    // a_odd  * b_odd   -> even columns, carry at limb i + 10
     }
-    // v = e + (o << 32)
+    // v = e + (o << 32) + (cw << 256)
     uint32_t v[16];
     v[0] = e[0];
     add_cc(v[1], e[1], o[0]);
 #pragma unroll
-    for (int i = 2; i < 16; i++) addc_cc(v[i], e[i], o[i - 1]);
+    for (int i = 2; i < 15; i++) addc_cc(v[i], e[i], o[i - 1]);
+    addc(v[15], e[15], o[14]);
+    add_cc(v[8], v[8], cw[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) addc_cc(v[8 + i], v[8 + i], cw[i]);
+    addc(v[15], v[15], cw[7]);
     reduce512(r, v);
 }
 
