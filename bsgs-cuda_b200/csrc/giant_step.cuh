@@ -39,11 +39,23 @@
 #ifndef GS_FP_HALF2
 #define GS_FP_HALF2 1
 #endif
+// GS_ABLATE: timing experiments only (results are wrong): bit 0 = no probe drain, bit 1 = no chain
+// traffic, bit 2 = giants read once per thread.  0 in every shipped build.
+#ifndef GS_ABLATE
+#define GS_ABLATE 0
+#endif
 
 namespace gs {
 
 constexpr int kMaxW = 16;
-constexpr int kRing = 16;                  // keys per thread between drains (2 per point-window)
+#ifndef GS_RING
+#define GS_RING 16
+#endif
+#ifndef GS_GROUP
+#define GS_GROUP 4
+#endif
+constexpr int kRing = GS_RING;             // keys per thread between drains (2 per point-window)
+constexpr int kGroup = GS_GROUP;           // independent sector loads in flight per thread during a drain
 
 // per-window constants, all canonical, little-endian limbs
 struct WinConst {
@@ -259,7 +271,7 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
         uint4* cp = tb.chain + t;
 #pragma unroll 1
         for (int r = 0; r < PP; r++, gxp += NT2) {
-            const Fe qx = ldg_fe(gxp, gxp + NT);
+            const Fe qx = ldg_fe((GS_ABLATE & 4) ? tb.gx + t : gxp, (GS_ABLATE & 4) ? tb.gx + t + NT : gxp + NT);
             const uint32_t* sw = s_win;
 #pragma unroll 1
             for (int w = 0; w < W; w++, sw += 32, cp += NT2) {
@@ -267,7 +279,7 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
                 { Fe px = lds_fe(sw); fp::fe_sub_canon(d.v, px.v, qx.v); }
                 if (fp::fe_is_zero_rare(d.v)) d = lds_fe(sw + 24);                          // 2*Py
                 Fe n; fp::fe_mul(n.v, acc.v, d.v); acc = n;
-                st8_stream(cp, cp + NT, acc.v);
+                if (!(GS_ABLATE & 2)) st8_stream(cp, cp + NT, acc.v);
             }
         }
     }
@@ -292,16 +304,18 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
     for (int ci = PP * W - 1; ci >= 0; ci--) {
         Fe cprev;                                                  // chain[ci-1], or 1 for the very first element
         cp -= NT2;
-        if (ci > 0) {
+        if (ci > 0 && !(GS_ABLATE & 2)) {
             ld8_stream(cprev.v, cp, cp + NT);
             if (ci > 1) { prefetch_l2(cp - NT2); prefetch_l2(cp - NT); }
+        } else if (GS_ABLATE & 2) {
+            cprev = inv;
         } else {
             cprev.v[0] = 1;
 #pragma unroll
             for (int i = 1; i < 8; i++) cprev.v[i] = 0;
         }
         if (sw == sw_top) {                                         // new row: slot (r, t) lives at (2r)*NT + t = 2*kidx - t
-            const size_t go = 2 * (size_t)kidx - t;
+            const size_t go = (GS_ABLATE & 4) ? (size_t)t : 2 * (size_t)kidx - t;
             qx = ldg_fe(tb.gx + go, tb.gx + go + NT); qy = ldg_fe(tb.gy + go, tb.gy + go + NT);
             if (MODE == 0 && kidx >= tb.N) special = true;
         }
@@ -339,28 +353,29 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
         }
         if (MODE == 0) {
             fill += 2;
+            if ((fill == kRing || ci == 0) && (GS_ABLATE & 1)) { fill = 0; special = false; }
             if (fill == kRing || ci == 0) {
                 // drain: slot 2j / 2j+1 = minus / plus key of chain index ci_first - j
                 const int ci_first = ci + (fill >> 1) - 1;
                 if (ci == 0) special = true;                        // the last burst may end inside a group of four
 #pragma unroll 1
-                for (int s0 = 0; s0 < fill; s0 += 4) {
-                    FpSector sec[4]; uint64_t key[4];
+                for (int s0 = 0; s0 < fill; s0 += kGroup) {
+                    FpSector sec[kGroup]; uint64_t key[kGroup];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
+                    for (int j = 0; j < kGroup; j++) {
                         key[j] = ring[(s0 + j) * BLOCK];
                         sec[j].load(tb, (uint32_t)key[j] & tb.mask);
                     }
-                    uint32_t need = special ? 15u : 0u;
+                    uint32_t need = special ? (1u << kGroup) - 1u : 0u;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) need |= (sec[j].maybe((uint32_t)(key[j] >> 32)) ? 1u : 0u) << j;
+                    for (int j = 0; j < kGroup; j++) need |= (sec[j].maybe((uint32_t)(key[j] >> 32)) ? 1u : 0u) << j;
                     // One warp-wide vote per group; the rare branch ends in an explicit __syncwarp(): without
                     // it lanes that took the out-of-line path were observed (ncu: 31.93 active lanes in the
                     // arithmetic, one SM busy 3x longer than the rest) to stay split from their warp for the
                     // remainder of the loop.
                     if (__any_sync(0xFFFFFFFFu, need != 0u)) {
 #pragma unroll 1
-                        for (int j = 0; j < 4; j++)
+                        for (int j = 0; j < kGroup; j++)
                             if ((need >> j) & 1u) drain_slow(tb, s_win, W, t, ci_first, s0 + j, fill, key[j]);
                         __syncwarp();
                     }
