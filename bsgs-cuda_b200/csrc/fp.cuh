@@ -285,6 +285,31 @@ FP_DEV uint64_t fe_add_low64_canon(const uint32_t a[8], const uint32_t u[8]) {
     return ((uint64_t)l1 << 32) | l0;
 }
 
+// Low 64 bits of the CANONICAL value of (L + A - Q) mod p without forming the 256-bit sum:
+// L lazy (< 2^256), A and Q canonical (< p).  (The kernel uses it with L = lambda^2, A = p - Px, Q = Qx:
+// X = lambda^2 - Px - Qx.)
+//
+// Write V = L + A - Q = S*2^224 + R with S = L[7] + A[7] - Q[7] (top limbs, -(2^32-1) <= S <= 2^33-2)
+// and R the same expression on the low 224 bits, -2^224 < R < 2^225.  Then
+//     S <= -2                      =>  V < 0,                 V mod p = V + p = V + 2^256 - C
+//     1 <= S <= 2^32 - 3           =>  0 <= V < 2^256 - 2^224 < p, V mod p = V
+//     2^32 + 1 <= S <= 2^33 - 4    =>  2^256 <= V < 2^256 + p - 2^224... , V mod p = V - 2^256 + C
+// (C = 2^32 + 977), and 2^256 does not reach the low 64 bits: key = (L + A - Q mod 2^64) + K*C with
+// K = -1, 0, +1.  For the seven remaining values of S (probability about 2^-29) the caller takes the
+// exact path (fe_sub_canon + fe_add_low64_canon).  t_lo = (A - Q) mod 2^64 and t7 = A[7] - Q[7] are
+// shared by the two candidates of a point-window.
+FP_DEV uint64_t fe_key_low64(const uint32_t L[8], uint64_t t_lo, int64_t t7, bool& exact_needed) {
+    const int64_t S = (int64_t)L[7] + t7;
+    const int64_t B = (int64_t)1 << 32;
+    const uint64_t lo = ((((uint64_t)L[1]) << 32) | L[0]) + t_lo;
+    exact_needed = (S >= -1 && S <= 0) || (S >= B - 2 && S <= B) || (S >= 2 * B - 3);
+    const uint64_t C = ((uint64_t)1 << 32) + FP_C0;
+    uint64_t key = lo;
+    if (S > B) key = lo + C;
+    if (S < 0) key = lo - C;
+    return key;
+}
+
 // a^(p-2) mod p with the 255-squaring / 15-multiplication addition chain for
 // p - 2 = 2^256 - 2^32 - 979 (the reference kernel uses plain right-to-left binary
 // exponentiation with 255 + 249 generic multiplications, PTX197:L1319-26062).

@@ -10,4 +10,12 @@ void he_add_lazy(uint32_t* r, const uint32_t* a, const uint32_t* b) { fp::fe_add
 void he_canon(uint32_t* r) { fp::fe_canon(r); }
 void he_reduce512(uint32_t* r, const uint32_t* v16) { uint32_t v[16]; for (int i = 0; i < 16; i++) v[i] = v16[i]; fp::reduce512(r, v); }
 uint64_t he_add_low64_canon(const uint32_t* a, const uint32_t* u) { return fp::fe_add_low64_canon(a, u); }
+// returns the key; *exact_needed = 1 when the caller must take the exact path
+uint64_t he_key_low64(const uint32_t* L, const uint32_t* A, const uint32_t* Q, int* exact_needed) {
+    const uint64_t a_lo = ((uint64_t)A[1] << 32) | A[0], q_lo = ((uint64_t)Q[1] << 32) | Q[0];
+    bool ex = false;
+    uint64_t k = fp::fe_key_low64(L, a_lo - q_lo, (int64_t)A[7] - (int64_t)Q[7], ex);
+    *exact_needed = ex ? 1 : 0;
+    return k;
+}
 }

@@ -206,6 +206,13 @@ struct FpSector {
 
 // exact, slow: Px == Qx (true doubling -> code 4), PTX197:L28996-
 __device__ __noinline__ uint64_t double_x_low64_v(Fe px, Fe inv2y) { return double_x_low64(px.v, inv2y.v); }
+// exact, slow: low 64 bits of canonical lambda^2 - Px - Qx for the few top-limb patterns that
+// fp::fe_key_low64 does not decide (about 2^-29 of the candidates)
+__device__ __noinline__ uint64_t key_exact(Fe l2, Fe npx, Fe qx) {
+    uint32_t u[8];
+    fp::fe_sub_canon(u, npx.v, qx.v);
+    return fp::fe_add_low64_canon(l2.v, u);
+}
 
 // Rare half of the drain: everything about ring slot `slot` of a burst is recomputed from its chain
 // index cj = ci_first - slot/2 (row cj / W, window cj % W) -- whether the row is padding (giant index
@@ -328,8 +335,10 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
         { Fe x; fp::fe_mul(x.v, inv.v, d.v); inv = x; }            // 1 / (d_0 ... d_{ci-1})
         uint64_t* rp = ring + fill * BLOCK;
         if (!eq) {
-            Fe u;
-            { Fe npx = lds_fe(sw + 16); fp::fe_sub_canon(u.v, npx.v, qx.v); }                      // -(Px + Qx)
+            // X = lambda^2 + (p - Px) - Qx is never formed: its low 64 bits follow from the low 64 bits and
+            // the top limbs of the three terms (fp::fe_key_low64); the part common to both candidates:
+            const uint64_t t_lo = *reinterpret_cast<const uint64_t*>(sw + 16) - (((uint64_t)qx.v[1] << 32) | qx.v[0]);
+            const int64_t t7 = (int64_t)sw[23] - (int64_t)qx.v[7];
 #pragma unroll
             for (int side = 0; side < 2; side++) {                  // side 0: P - Q (code 2), slope (Py + Qy)/d ; side 1: P + Q (code 1), slope (Py - Qy)/d
                 Fe py = lds_fe(sw + 8), sum, lam, l2;
@@ -337,7 +346,9 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
                 else fp::fe_sub_canon(sum.v, py.v, qy.v);
                 fp::fe_mul(lam.v, sum.v, invd.v);
                 fp::fe_sqr(l2.v, lam.v);
-                const uint64_t key = fp::fe_add_low64_canon(l2.v, u.v);
+                bool exact_needed;
+                uint64_t key = fp::fe_key_low64(l2.v, t_lo, t7, exact_needed);
+                if (exact_needed) key = key_exact(l2, lds_fe(sw + 16), qx);
                 if (MODE == 0) rp[side * BLOCK] = key;
                 else if (kidx < tb.N) {                             // multiplier C - (i+1) (side 0) or C + (i+1) (side 1)
                     const uint64_t i1 = (uint64_t)kidx + 1, c = wp.center[(sw - s_win) >> 5];

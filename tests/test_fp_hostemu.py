@@ -103,3 +103,44 @@ def test_reduce512_all_branches(he):
         r = limbs(0)
         he.he_reduce512(r, arr)
         assert val(r) % P == v % P, hex(v)
+
+
+def test_key_low64_by_top_limb_classification(he):
+    """fe_key_low64: low 64 bits of canonical (L + A - Q) from the low 64 bits and the top limbs only.
+    Whenever it does not ask for the exact path its answer must be exact -- checked on random inputs
+    and on inputs crafted around every boundary of the classification (S = L7 + A7 - Q7 near 0, 2^32,
+    2^33) with the low 224 bits at their extremes."""
+    he.he_key_low64.restype = C.c_uint64
+    rnd = random.Random(12)
+    B = 1 << 32
+    lows = [0, 1, 2**224 - 1, 2**224 - 2, 2**223, 2**64 - 1, 2**64, 977]
+    cases = []
+    for _ in range(3000):
+        cases.append((rnd.getrandbits(256), rnd.randrange(P), rnd.randrange(P)))
+    for S in [-3, -2, -1, 0, 1, 2, B - 4, B - 3, B - 2, B - 1, B, B + 1, B + 2, 2 * B - 5, 2 * B - 4, 2 * B - 3, 2 * B - 2]:
+        for _ in range(40):
+            # pick top limbs with L7 + A7 - Q7 == S
+            for _try in range(100):
+                l7, q7 = rnd.randrange(B), rnd.randrange(B)
+                a7 = S - l7 + q7
+                if 0 <= a7 < B:
+                    break
+            else:
+                continue
+            lo = [rnd.choice(lows + [rnd.getrandbits(224)]) for _ in range(3)]
+            L = (l7 << 224) | lo[0]; A = (a7 << 224) | lo[1]; Q = (q7 << 224) | lo[2]
+            if A < P and Q < P:
+                cases.append((L, A, Q))
+    assert len(cases) > 3300
+    asked = 0
+    for L, A, Q in cases:
+        ex = C.c_int()
+        k = he.he_key_low64(limbs(L), limbs(A), limbs(Q), C.byref(ex))
+        S = (L >> 224) + (A >> 224) - (Q >> 224)
+        want_exact = S in (-1, 0, B - 2, B - 1, B, 2 * B - 3, 2 * B - 2)
+        assert bool(ex.value) == want_exact, hex(S)
+        if ex.value:
+            asked += 1
+        else:
+            assert k == ((L + A - Q) % P) & M64, (hex(L), hex(A), hex(Q))
+    assert 0 < asked < len(cases) // 3
