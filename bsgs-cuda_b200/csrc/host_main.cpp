@@ -349,7 +349,9 @@ struct Search {
     }
     U256 window_key(uint64_t j) const { return addmod(key0, mod_n(mul_small(rank_stride, j))); }
     Pt window_point(uint64_t j) const { if (!j) return P0; Pt r, s = pt_mul(D, from_u64(j)); hec::pt_add(r, P0, s); return r; }
-    // GetJob is called until key_j > pke - pk, tested after the launch (1_9_7File.pb:2512-2518)
+    // The reference tests key_j > pke - pk AFTER the launch of window j (1_9_7File.pb:2512-2518): every window
+    // with key_j <= width is launched and then one more, which holds the tail of the range (window j covers
+    // key_j + p*w +- (2Nw + w) only).
     uint64_t windows_needed(const U256& pke, const U256& start_key) const {
         U256 width; sub_raw(width, pke, pk);
         uint64_t total = 1;
@@ -358,11 +360,12 @@ struct Search {
             // floor(d / stride): stride < 2^66 and d / stride < 2^64 for every range this program accepts in practice
             long double q = 0; for (int i = 3; i >= 0; i--) q = q * 18446744073709551616.0L + (long double)d.v[i];
             long double sd = (long double)stride.v[1] * 18446744073709551616.0L + (long double)stride.v[0];
+            if (q / sd >= 9.0e18L) throw UsageError{"Range is too wide for these -t/-b/-p/-w: more than 2^63 windows"};
             uint64_t est = (uint64_t)(q / sd);
             // exact correction around the floating-point estimate
             while (est > 0 && cmp(mul_small(stride, est), d) > 0) est--;
             while (cmp(mul_small(stride, est + 1), d) <= 0) est++;
-            total = est + 1;
+            total = est + 2;
         }
         return total > (uint64_t)rank ? (total - rank + world - 1) / world : 0;
     }
@@ -449,10 +452,13 @@ int run(const std::vector<std::string>& argv) {
         logln("Searchpubkey: " + compress(searches[0].findpub));
         std::mutex mu; std::atomic<bool> stop{false}; bool have_key = false; U256 key;
         std::vector<uint64_t> done(R, 0); unsigned long long steps = 0;
+        std::vector<uint64_t> nwins(R, 0);
+        try { for (int r = 0; r < R; r++) nwins[r] = searches[r].windows_needed(o.pke, start_key); }
+        catch (const UsageError& e) { logln(e.msg); rc = 2; break; }
         const auto t_begin = std::chrono::steady_clock::now();
         auto worker = [&](int r) {
             const Search& s = searches[r];
-            const uint64_t nwin = s.windows_needed(o.pke, start_key);
+            const uint64_t nwin = nwins[r];
             std::vector<bsgs_hit> hits(4096);
             uint64_t d0 = 0;
             while (d0 < nwin && !stop) {
@@ -462,6 +468,8 @@ int run(const std::vector<std::string>& argv) {
                 uint32_t nh = 0; uint64_t wd = 0;
                 int e = bsgs_run(ctx[r], p0, dd, chunk, chunk, 1, hits.data(), (uint32_t)hits.size(), &nh, &wd);
                 if (e != BSGS_OK && e != BSGS_E_OVERFLOW) { fprintf(stderr, "bsgs_run: %s\n", bsgs_strerror(e)); stop = true; return; }
+                if (e == BSGS_E_OVERFLOW && hits.size() < (1u << 22)) { hits.resize(hits.size() * 4); continue; }      // rerun this chunk with a bigger record buffer
+                nh = std::min<uint32_t>(nh, (uint32_t)hits.size());
                 for (uint32_t i = 0; i < nh; i++) {
                     U256 fin;
                     if (hits[i].reserved != 0xFFFFFFFFu && s.check_record(hits[i].code, hits[i].idx, d0 + hits[i].window, hits[i].reserved, fin)) {

@@ -34,9 +34,11 @@ class Search:
         return ec.add(self.P0, ec.mul(self.D, j)) if j else self.P0
 
     def windows_needed(self, pke):
-        """GetJob is called until key_j > pke - pk, tested after the launch (1_9_7File.pb:2512-2518)."""
+        """The reference tests key_j > pke - pk AFTER the launch of window j (1_9_7File.pb:2512-2518), so it
+        launches every window with key_j <= width and then one more: window j only covers
+        key_j + p*w +- (2Nw + w), and the tail of the range lies in that last window."""
         width = pke - self.pk
-        total = max((width - self.start_key) // self.stride + 1, 1) if width >= self.start_key else 1
+        total = (width - self.start_key) // self.stride + 2 if width >= self.start_key else 1
         return (total - self.rank + self.world - 1) // self.world if total > self.rank else 0
 
     # ---- checkerThread

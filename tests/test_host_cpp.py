@@ -161,3 +161,28 @@ def test_tune_lines_equal_the_python_mirror(exe, mem, sm, major, minor):
     if o:
         want.append(tune.format_try(o) + "   (this build)")
     assert lines[1:] == want
+
+
+@pytest.mark.gpu
+def test_both_hosts_find_a_key_in_the_last_half_stride(exe, tmp_path):
+    """The reference tests the end of the range AFTER a launch (1_9_7File.pb:2512-2518): the window whose
+    key first exceeds pke - pk is still searched and holds the tail of the range."""
+    import io
+    T, B, p, wl, htsz = 32, 4, 16, 12, 10
+    w = 1 << wl
+    stride = 4 * T * B * p * w
+    pk = 0x4000000000
+    for tail in (stride // 2 - 3, 5 * w):                 # distance of the key below pke
+        width = 3 * stride + stride // 4                   # est = 3 -> 5 launches; the key lies beyond window 3's reach
+        secret = pk + width - tail
+        pt = pyec.mul(pyec.G, secret)
+        args = f"-t {T} -b {B} -p {p} -w {wl} -htsz {htsz} -pk {pk:x} -pke {pk + width:x} -nosave -pb {b.ec.compress(pt)}".split()
+        rc, out = run(exe, args, cwd=tmp_path)
+        assert rc == 0 and f"KEY[1]: 0x{secret:064x}" in out, out
+        buf = io.StringIO()
+        cwd = os.getcwd(); os.chdir(tmp_path)
+        try:
+            assert b.cli.main(args, out=buf) == 0
+        finally:
+            os.chdir(cwd)
+        assert f"0x{secret:064x}" in buf.getvalue(), buf.getvalue()

@@ -81,3 +81,62 @@ def test_check_hit_equals_oracle_checker(orc, seed):
                     assert mine == secret
                     found += 1
     assert found >= 8
+
+
+def _ref_loop_launch_count(orc, T, B, p, w, htsz, pk, pke, target):
+    """cuda()'s loop as written (1_9_7File.pb:2402-2523): launch window j, THEN break if key_j > pke - pk,
+    else GetJob."""
+    o = orc.SearchState(T, B, p, w, htsz, pk, target)
+    width = pke - pk
+    launches = 0
+    while True:
+        key, _ = o.get_job()
+        launches += 1
+        if key > width:
+            return launches
+
+
+@pytest.mark.parametrize("T,B,p,w,pk,width", [(2, 2, 4, 8, 1, 500), (2, 2, 4, 8, 1, 511), (2, 2, 4, 8, 1, 512), (2, 2, 4, 8, 1, 513), (2, 2, 4, 8, 77, 0),
+                                              (4, 3, 2, 100, 1 << 40, 123457), (8, 3, 6, 777, 0x8000000000, 0x7fffffffff)])
+def test_windows_needed_equals_the_reference_loop_and_covers_the_range(orc, T, B, p, w, pk, width):
+    """The end-of-range test runs after the launch, so the window whose key first exceeds the width is
+    still launched -- it holds the tail of [pk, pke] (with T=2,B=2,p=4,w=8,pk=1,pke=501 the offset
+    400 lies only in window 1)."""
+    N = T * B * p
+    target = pyec.mul(pyec.G, pk + 5)
+    s = b.Search(T, B, p, w, 5, pk, target)
+    n = s.windows_needed(pk + width)
+    if width < (1 << 24):
+        assert n == _ref_loop_launch_count(orc, T, B, p, w, 5, pk, pk + width, target)
+    else:
+        assert n == (width - 1) // s.stride + 2
+    # coverage: window j reaches key_j + p*w +- (2Nw + w); consecutive windows overlap; the union holds [1, width]
+    lo = s.window_key(0) + s.centerbig - (2 * N * w + w)
+    hi = s.window_key(n - 1) + s.centerbig + (2 * N * w + w)
+    assert lo <= 1 and hi >= width
+    for j in range(min(n - 1, 50)):
+        assert s.window_key(j + 1) + s.centerbig - (2 * N * w + w) <= s.window_key(j) + s.centerbig + (2 * N * w + w) + 1
+    # ranks partition exactly that count
+    for R in (2, 3):
+        assert sum(b.Search(T, B, p, w, 5, pk, target, rank=r, world=R).windows_needed(pk + width) for r in range(R)) == n
+
+
+def test_key_in_the_last_half_stride_is_found_by_the_cpu_model(orc):
+    """Keys planted near pke are recovered when exactly windows_needed() windows are searched."""
+    T, B, p, w, htsz = 2, 2, 4, 8, 4
+    N = T * B * p
+    keys = orc.baby_keys(w)
+    cpu, gpu = orc.build_ht(keys, htsz)
+    g2 = orc.build_g2(T, B, p, w)
+    pk = 1
+    for pke, secret_off in ((501, 400), (501, 499), (1025, 1024), (700, 650)):
+        target = pyec.mul(pyec.G, pk + secret_off)
+        s = b.Search(T, B, p, w, htsz, pk, target)
+        found = None
+        for j in range(s.windows_needed(pke)):
+            P = s.window_point(j)
+            if P is None:
+                continue
+            for code, idx in orc.launch(g2, T, B, p, gpu, htsz, P):
+                found = found or s.check_hit(cpu, code, idx, j)
+        assert found == pk + secret_off, (pke, secret_off, found)
