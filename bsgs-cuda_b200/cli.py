@@ -175,6 +175,7 @@ def list_devices(log):
 
 def main(argv=None, out=sys.stdout) -> int:
     log = lambda s: (out.write(s + "\n"), out.flush())               # noqa: E731
+    t_program = time.time()                                          # begintime, 1_9_7File.pb:5135 (Tt:)
     try:
         o = parse_args(list(sys.argv[1:] if argv is None else argv))
         for wmsg in validate(o):
@@ -222,7 +223,7 @@ def main(argv=None, out=sys.stdout) -> int:
             log(""); log(f"Findpubkey  : {ec.compress(target)}")
             searches = [Search(T, B, p, w, htsz, o["pk"], target, start_key=start_key, rank=r, world=R) for r in range(R)]
             log(f"Searchpubkey: {ec.compress(searches[0].findpub)}")
-            state = dict(key=None, stop=False, done=[0] * R, steps=0, lock=threading.Lock())
+            state = dict(key=None, stop=False, done=[0] * R, steps=[0] * R, lock=threading.Lock())
             t_begin = time.time()
 
             def worker(r):
@@ -244,7 +245,7 @@ def main(argv=None, out=sys.stdout) -> int:
                                 state["key"], state["stop"] = k, True
                     done += d
                     with state["lock"]:
-                        state["done"][r] = done; state["steps"] += 2 * s.N * d
+                        state["done"][r] = done; state["steps"][r] += 2 * s.N * d
 
             def saver():                                             # saveCurentCNT, 1_9_7File.pb:3897-3931
                 last = time.time()
@@ -258,7 +259,7 @@ def main(argv=None, out=sys.stdout) -> int:
             sv = threading.Thread(target=saver, daemon=True); sv.start()
             for th in threads:
                 th.start()
-            last_log = time.time(); last_steps = 0
+            last_log = time.time(); last_steps = [0] * R
             while True:
                 alive = [th for th in threads if th.is_alive()]
                 if not alive:
@@ -266,12 +267,11 @@ def main(argv=None, out=sys.stdout) -> int:
                 alive[0].join(0.05)                                  # returns at once when the worker ends (no polling quantum per target)
                 if time.time() - last_log > 2:                       # status line, 1_9_7File.pb:5119-5141
                     with state["lock"]:
-                        st = state["steps"]
-                    rate = (st - last_steps) / (time.time() - last_log); last_steps = st; last_log = time.time()
+                        st = list(state["steps"])
+                    dt = time.time() - last_log
+                    rates = [(a - c) / dt for a, c in zip(st, last_steps)]; last_steps = st; last_log = time.time()
                     cnt = min(searches[r].window_key(state["done"][r]) for r in range(R))
-                    wald = math.log2(2 * w)
-                    log(f"Cnt:{cnt:x} [{R}] = {int(rate) >> 20} MKeys/s x2^{wald:.1f}=2^{(math.log2(rate) if rate > 0 else 0) + wald:.2f} "
-                        f"Jt:{time.strftime('%H:%M:%S', time.gmtime(time.time() - t_begin))}")
+                    log(format_status(cnt, len(alive), rates, w, time.time() - t_begin, time.time() - t_program))
             state["stop"] = True
             if state["key"] is not None:
                 tag = f"KEY[{listpos}]: "
@@ -289,6 +289,22 @@ def main(argv=None, out=sys.stdout) -> int:
     finally:
         for e in engines:
             e.close()
+
+
+def _hms(sec):
+    sec = int(sec)
+    return f"{sec // 3600 % 24:02d}:{sec // 60 % 60:02d}:{sec % 60:02d}"
+
+
+def format_status(cnt, running, rates, w, job_s, total_s):
+    """The status line of the main loop (1_9_7File.pb:5119-5141): counter, workers alive, giant steps/s of
+    every GPU and in total in units of 2^20, the keys each step covers (2w), job time and total time."""
+    total = sum(int(r) for r in rates)
+    wald = math.log2(2 * w)
+    hashd = math.log2(total) if total else 0
+    perf = "".join(f"{int(r) >> 20} " for r in rates)
+    return (f"Cnt:{cnt:x} [{running}][ {perf}] = {total >> 20} MKeys/s x2^{wald:.1f}=2^{hashd + wald:.2f} "
+            f"Jt:{_hms(job_s)} Tt:{_hms(total_s)}")
 
 
 def save_checkpoint(listpos, pub_full_hex, cnt, fp, path="currentwork.txt"):

@@ -672,3 +672,25 @@ extern "C" int bsgs_debug_field(int device, int op, const uint32_t* a, const uin
     if (e != cudaSuccess) { cudaGetLastError(); return BSGS_E_CUDA; }
     return BSGS_OK;
 }
+
+// the hot loop's key extraction on arbitrary (L, A, Q) triples: keys[i] = low 64 bits of canonical
+// (L + A - Q) mod p, exact[i] = 1 when the out-of-line exact path ran
+extern "C" int bsgs_debug_key(int device, const uint32_t* L, const uint32_t* A, const uint32_t* Q, uint64_t* keys, uint8_t* exact, uint32_t n) {
+    if (!L || !A || !Q || !keys || !exact || !n) return BSGS_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return BSGS_E_CUDA;
+    uint32_t *dl = nullptr, *da = nullptr, *dq = nullptr; uint64_t* dk = nullptr; uint8_t* de = nullptr; size_t bytes = (size_t)n * 32;
+    cudaError_t e = cudaMalloc(&dl, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&da, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&dq, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&dk, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&de, n);
+    if (e == cudaSuccess) e = cudaMemcpy(dl, L, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(da, A, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dq, Q, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { gs::k_debug_key<<<(n + 127) / 128, 128>>>(dl, da, dq, dk, de, n); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpy(keys, dk, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(exact, de, n, cudaMemcpyDeviceToHost);
+    cudaFree(dl); cudaFree(da); cudaFree(dq); cudaFree(dk); cudaFree(de);
+    if (e != cudaSuccess) { cudaGetLastError(); return BSGS_E_CUDA; }
+    return BSGS_OK;
+}

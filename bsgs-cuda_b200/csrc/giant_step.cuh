@@ -214,6 +214,19 @@ __device__ __noinline__ uint64_t key_exact(Fe l2, Fe npx, Fe qx) {
     return fp::fe_add_low64_canon(l2.v, u);
 }
 
+// The key of one candidate as the hot loop computes it: low 64 bits of canonical l2 + npx - qx, from
+// the low 64 bits and the top limbs (fp::fe_key_low64) with the out-of-line exact path for the few
+// top-limb patterns that does not decide.  `npx` points at the eight limbs of p - Px (shared memory in
+// the kernel).  k_debug_key runs exactly this function on arbitrary inputs (tests: the exact path
+// fires about 48 times per second per GPU in production and essentially never at test sizes).
+__device__ __forceinline__ uint64_t candidate_key(const Fe& l2, uint64_t t_lo, int64_t t7, const uint32_t* npx, const Fe& qx, bool* took_exact = nullptr) {
+    bool exact_needed;
+    uint64_t key = fp::fe_key_low64(l2.v, t_lo, t7, exact_needed);
+    if (exact_needed) key = key_exact(l2, lds_fe(npx), qx);
+    if (took_exact) *took_exact = exact_needed;
+    return key;
+}
+
 // Rare half of the drain: everything about ring slot `slot` of a burst is recomputed from its chain
 // index cj = ci_first - slot/2 (row cj / W, window cj % W) -- whether the row is padding (giant index
 // >= N), whether the pair was a tangent (Px == Qx: slot 2j holds X(2P), code 4, and slot 2j+1 is
@@ -346,9 +359,7 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
                 else fp::fe_sub_canon(sum.v, py.v, qy.v);
                 fp::fe_mul(lam.v, sum.v, invd.v);
                 fp::fe_sqr(l2.v, lam.v);
-                bool exact_needed;
-                uint64_t key = fp::fe_key_low64(l2.v, t_lo, t7, exact_needed);
-                if (exact_needed) key = key_exact(l2, lds_fe(sw + 16), qx);
+                const uint64_t key = candidate_key(l2, t_lo, t7, sw + 16, qx);
                 if (MODE == 0) rp[side * BLOCK] = key;
                 else if (kidx < tb.N) {                             // multiplier C - (i+1) (side 0) or C + (i+1) (side 1)
                     const uint64_t i1 = (uint64_t)kidx + 1, c = wp.center[(sw - s_win) >> 5];
@@ -468,6 +479,23 @@ __global__ void k_debug_field(int op, const uint32_t* a, const uint32_t* b, uint
     }
 #pragma unroll
     for (int j = 0; j < 8; j++) r[8 * i + j] = z[j];
+}
+
+// diagnostics: the hot loop's key extraction (candidate_key: fe_key_low64 + key_exact) on arbitrary
+// triples (L lazy, A and Q canonical), formed exactly as PASS 2 forms them
+__global__ void k_debug_key(const uint32_t* L, const uint32_t* A, const uint32_t* Q, uint64_t* keys, uint8_t* exact, uint32_t n) {
+    __shared__ __align__(16) uint32_t s_a[128 * 8];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fe l2, qx;
+    uint32_t* a = s_a + threadIdx.x * 8;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { l2.v[j] = L[8 * i + j]; qx.v[j] = Q[8 * i + j]; a[j] = A[8 * i + j]; }
+    const uint64_t t_lo = *reinterpret_cast<const uint64_t*>(a) - (((uint64_t)qx.v[1] << 32) | qx.v[0]);
+    const int64_t t7 = (int64_t)a[7] - (int64_t)qx.v[7];
+    bool ex;
+    keys[i] = candidate_key(l2, t_lo, t7, a, qx, &ex);
+    exact[i] = ex ? 1 : 0;
 }
 
 }  // namespace gs

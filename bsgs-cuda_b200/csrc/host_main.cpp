@@ -149,6 +149,7 @@ uint64_t parse_w(const std::string& arg) {                                // 1_9
     double v = atof(arg.c_str());
     return v <= 32 ? (uint64_t)pow(2.0, v) : strtoull(arg.c_str(), nullptr, 10);
 }
+std::string format_status(const std::string& cnt_hex, int running, const std::vector<unsigned long long>& rates, uint64_t w, double job_s, double total_s);
 Options parse_args(const std::vector<std::string>& argv) {
     Options o; parse_hex("1ffffffffffffffff", o.pke);
     for (size_t i = 0; i < argv.size(); i++) {
@@ -163,6 +164,13 @@ Options parse_args(const std::vector<std::string>& argv) {
             unsigned long long mem = 0; int sm = 0, mj = 0, mn = 0;
             if (!has || sscanf(val.c_str(), "%llu,%d,%d,%d", &mem, &sm, &mj, &mn) != 4) throw UsageError{"-tune free_bytes,sm,major,minor"};
             print_try(mem, sm, mj, mn); exit(0);
+        }
+        if (a == "-statusline") {                                            // extension used by the tests: -statusline cnthex,running,w,job_s,total_s,rate0[,rate1...]
+            std::vector<std::string> f; std::string v = val + ","; size_t q;
+            while ((q = v.find(',')) != std::string::npos) { f.push_back(v.substr(0, q)); v.erase(0, q + 1); }
+            if (f.size() < 6) throw UsageError{"-statusline cnthex,running,w,job_s,total_s,rate0[,rate1...]"};
+            std::vector<unsigned long long> rates; for (size_t k = 5; k < f.size(); k++) rates.push_back(strtoull(f[k].c_str(), nullptr, 10));
+            puts(format_status(f[0], atoi(f[1].c_str()), rates, strtoull(f[2].c_str(), nullptr, 10), atof(f[3].c_str()), atof(f[4].c_str())).c_str()); exit(0);
         }
         if (a == "-t") { if (has) { o.t = (uint32_t)atoi(val.c_str()); i++; } }
         else if (a == "-b") { if (has) { o.b = (uint32_t)atoi(val.c_str()); i++; } }
@@ -398,9 +406,19 @@ void save_checkpoint(int listpos, const std::string& pub_full_hex, const U256& c
     FILE* f = fopen("currentwork.temp", "w"); if (!f) return;
     fputs(body.c_str(), f); fclose(f); rename("currentwork.temp", "currentwork.txt");
 }
-std::string fmt_hms(double s) { int t = (int)s; char b[32]; snprintf(b, sizeof b, "%02d:%02d:%02d", t / 3600, (t / 60) % 60, t % 60); return b; }
+std::string fmt_hms(double s) { int t = (int)s; char b[32]; snprintf(b, sizeof b, "%02d:%02d:%02d", (t / 3600) % 24, (t / 60) % 60, t % 60); return b; }
+// the status line of the main loop (1_9_7File.pb:5119-5141): counter, workers alive, giant steps/s of every
+// GPU and in total in units of 2^20, the keys each step covers (2w), job time and total time
+std::string format_status(const std::string& cnt_hex, int running, const std::vector<unsigned long long>& rates, uint64_t w, double job_s, double total_s) {
+    unsigned long long total = 0; std::string perf;
+    for (auto r : rates) { total += r; perf += std::to_string(r >> 20) + " "; }
+    const double wald = log2(2.0 * (double)w), hashd = total ? log2((double)total) : 0.0;
+    char buf[128]; snprintf(buf, sizeof buf, "] = %llu MKeys/s x2^%.1f=2^%.2f Jt:", total >> 20, wald, hashd + wald);
+    return "Cnt:" + cnt_hex + " [" + std::to_string(running) + "][ " + perf + buf + fmt_hms(job_s) + " Tt:" + fmt_hms(total_s);
+}
 
 int run(const std::vector<std::string>& argv) {
+    const auto t_program = std::chrono::steady_clock::now();             // begintime (Tt:), 1_9_7File.pb:5135
     Options o;
     std::vector<std::string> pubs;
     try {
@@ -451,7 +469,7 @@ int run(const std::vector<std::string>& argv) {
         for (int r = 0; r < R; r++) searches.emplace_back(o, target, start_key, r, R);
         logln("Searchpubkey: " + compress(searches[0].findpub));
         std::mutex mu; std::atomic<bool> stop{false}; bool have_key = false; U256 key;
-        std::vector<uint64_t> done(R, 0); unsigned long long steps = 0;
+        std::vector<uint64_t> done(R, 0); std::vector<unsigned long long> steps(R, 0);
         std::vector<uint64_t> nwins(R, 0);
         try { for (int r = 0; r < R; r++) nwins[r] = searches[r].windows_needed(o.pke, start_key); }
         catch (const UsageError& e) { logln(e.msg); rc = 2; break; }
@@ -477,7 +495,7 @@ int run(const std::vector<std::string>& argv) {
                     }
                 }
                 d0 += wd;
-                std::lock_guard<std::mutex> g(mu); done[r] = d0; steps += 2ull * s.N * wd;
+                std::lock_guard<std::mutex> g(mu); done[r] = d0; steps[r] += 2ull * s.N * wd;
             }
         };
         std::vector<std::thread> th;
@@ -485,18 +503,19 @@ int run(const std::vector<std::string>& argv) {
         std::atomic<int> alive{R};
         // status line + checkpoint from the main thread (1_9_7File.pb:5119-5141, 3897-3931)
         std::thread joiner([&] { for (auto& t : th) { t.join(); alive--; } });
-        auto last_log = std::chrono::steady_clock::now(), last_save = last_log; unsigned long long last_steps = 0;
+        auto last_log = std::chrono::steady_clock::now(), last_save = last_log; std::vector<unsigned long long> last_steps(R, 0);
         while (alive > 0) {
             std::this_thread::sleep_for(std::chrono::milliseconds(2));
             auto now = std::chrono::steady_clock::now();
             auto min_cnt = [&] { std::lock_guard<std::mutex> g(mu); U256 m = searches[0].window_key(done[0]); for (int r = 1; r < R; r++) { U256 k = searches[r].window_key(done[r]); if (cmp(k, m) < 0) m = k; } return m; };
             if (std::chrono::duration<double>(now - last_log).count() > 2) {
-                unsigned long long st; { std::lock_guard<std::mutex> g(mu); st = steps; }
-                double rate = (double)(st - last_steps) / std::chrono::duration<double>(now - last_log).count(); last_steps = st; last_log = now;
-                char buf[256]; double wald = log2(2.0 * (double)o.w);
-                snprintf(buf, sizeof buf, "Cnt:%s [%d] = %llu MKeys/s x2^%.1f=2^%.2f Jt:%s", hex_short(min_cnt()).c_str(), R, (unsigned long long)rate >> 20, wald,
-                         (rate > 0 ? log2(rate) : 0) + wald, fmt_hms(std::chrono::duration<double>(now - t_begin).count()).c_str());
-                logln(buf);
+                std::vector<unsigned long long> st; { std::lock_guard<std::mutex> g(mu); st = steps; }
+                const double dt = std::chrono::duration<double>(now - last_log).count();
+                std::vector<unsigned long long> rates(R);
+                for (int r = 0; r < R; r++) rates[r] = (unsigned long long)((double)(st[r] - last_steps[r]) / dt);
+                last_steps = st; last_log = now;
+                logln(format_status(hex_short(min_cnt()), (int)alive, rates, o.w, std::chrono::duration<double>(now - t_begin).count(),
+                                    std::chrono::duration<double>(now - t_program).count()));
             }
             if (std::chrono::duration<double>(now - last_save).count() >= o.wt) { save_checkpoint(listpos, full, min_cnt(), fp); last_save = now; }
         }

@@ -37,7 +37,7 @@ class DevInfo(C.Structure):
 EXPORTS = ["bsgs_create", "bsgs_destroy", "bsgs_strerror", "bsgs_last_cuda_error", "bsgs_upload_giants", "bsgs_upload_ht", "bsgs_upload_htcpu",
            "bsgs_giants_staging", "bsgs_giants_commit", "bsgs_ht_staging", "bsgs_ht_commit", "bsgs_step", "bsgs_step_multi",
            "bsgs_giants_generate", "bsgs_giants_export", "bsgs_ht_build_from_keys", "bsgs_ht_generate", "bsgs_ht_build_synthetic", "bsgs_ht_export", "bsgs_ht_device_image",
-           "bsgs_run", "bsgs_time_launches", "bsgs_probe_bench", "bsgs_probe_keys", "bsgs_get_info", "bsgs_set_option", "bsgs_debug_field", "bsgs_device_count", "bsgs_device_query", "bsgs_bcast_ht"]
+           "bsgs_run", "bsgs_time_launches", "bsgs_probe_bench", "bsgs_probe_keys", "bsgs_get_info", "bsgs_set_option", "bsgs_debug_field", "bsgs_debug_key", "bsgs_device_count", "bsgs_device_query", "bsgs_bcast_ht"]
 
 _lib = None
 
@@ -80,6 +80,7 @@ def load():
     L.bsgs_get_info.argtypes = [vp, C.POINTER(Info)]
     L.bsgs_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.bsgs_debug_field.argtypes = [C.c_int, C.c_int, vp, vp, vp, u32]
+    L.bsgs_debug_key.argtypes = [C.c_int, vp, vp, vp, vp, vp, u32]
     L.bsgs_bcast_ht.argtypes = [C.POINTER(vp), C.c_int]
     L.bsgs_device_count.argtypes = [C.POINTER(C.c_int)]
     L.bsgs_device_query.argtypes = [C.c_int, C.POINTER(DevInfo)]
@@ -124,6 +125,23 @@ def debug_field(op: int, a, b, device=0):
     if rc:
         raise BsgsError(rc, "bsgs_debug_field")
     return [sum(int(R[j, i]) << (32 * i) for i in range(8)) for j in range(n)]
+
+
+def _limbs(vals):
+    a = np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in vals), dtype=np.uint32)
+    return np.ascontiguousarray(a.reshape(len(vals), 8))
+
+
+def debug_key(Ls, As, Qs, device=0):
+    """The kernel's key extraction (candidate_key in giant_step.cuh) on triples (L, A, Q): returns
+    (keys, exact_flags) as numpy arrays."""
+    n = len(Ls)
+    L_, A_, Q_ = _limbs(Ls), _limbs(As), _limbs(Qs)
+    keys = np.zeros(n, dtype=np.uint64); ex = np.zeros(n, dtype=np.uint8)
+    rc = load().bsgs_debug_key(device, L_.ctypes.data, A_.ctypes.data, Q_.ctypes.data, keys.ctypes.data, ex.ctypes.data, n)
+    if rc:
+        raise BsgsError(rc, "bsgs_debug_key")
+    return keys, ex
 
 
 def _strerror(status):

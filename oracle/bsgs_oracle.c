@@ -8,6 +8,7 @@
  */
 #include "bsgs_oracle.h"
 #include <string.h>
+#include <time.h>
 #include <stdlib.h>
 #include <stdio.h>
 #include <math.h>
@@ -586,6 +587,19 @@ int orc_check_hit(const orc_search *s, const uint8_t *htcpu, const orc_hit *h,
         }
     }
     return 0;
+}
+
+/* The reference's own single-core sanity timing (Curve64.pb:3303-3320): b = G; n times b = G + b with
+ * m_ADDPTX64 (one binary-GCD inversion per addition).  Returns the elapsed seconds; *out = final b
+ * (n = 10000: x = db7432110ba8...65a8, the known answer of that block). */
+double orc_time_seq_adds(uint32_t n, orc_pt *out) {
+    struct timespec t0, t1;
+    orc_pt a = G_, b = G_;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (uint32_t i = 0; i < n; i++) orc_pt_add(&b, &a, &b);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (out) *out = b;
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
 uint64_t orc_parse_w(const char *arg) {                                  /* F197:1009-1022 */

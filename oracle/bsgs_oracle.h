@@ -109,6 +109,7 @@ int  orc_check_hit(const orc_search *s, const uint8_t *htcpu, const orc_hit *h,
 
 /* -w parser: value <= 32 means 2^x truncated, else decimal (1_9_7File.pb:1009-1022) */
 uint64_t orc_parse_w(const char *arg);
+double orc_time_seq_adds(uint32_t n, orc_pt *out);   /* Curve64.pb:3303-3320 */
 
 #ifdef __cplusplus
 }

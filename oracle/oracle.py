@@ -116,6 +116,7 @@ def lib():
         L.orc_check_hit.argtypes = [C.POINTER(Search), C.c_void_p, C.POINTER(Hit), pf, pp, pf]
         L.orc_check_hit.restype = C.c_int
         L.orc_parse_w.argtypes = [C.c_char_p]; L.orc_parse_w.restype = C.c_uint64
+        L.orc_time_seq_adds.argtypes = [C.c_uint32, C.POINTER(Pt)]; L.orc_time_seq_adds.restype = C.c_double
         _lib = L
     return _lib
 
@@ -176,6 +177,13 @@ def parse_pubkey(s: str):
 
 def parse_w(arg: str) -> int:
     return int(lib().orc_parse_w(arg.encode()))
+
+
+def time_seq_adds(n: int = 10000):
+    """Curve64.pb:3303-3320: n sequential affine additions b = G + b on one core -> (seconds, final point)."""
+    out = Pt()
+    dt = lib().orc_time_seq_adds(n, C.byref(out))
+    return dt, out.tup()
 
 
 def baby_keys(w: int, nthreads: int = 8) -> np.ndarray:

@@ -57,6 +57,47 @@ def test_low64_slow_path_on_device(pkg):
     assert [v & M64 for v in got] == [((x + y) % P) & M64 for x, y in zip(a, u)]
 
 
+def test_hot_loop_key_extraction_on_device_incl_the_exact_path(pkg):
+    """candidate_key (fe_key_low64 + out-of-line key_exact, giant_step.cuh) ON THE DEVICE, as PASS 2 calls
+    it: boundary cases of the top-limb classification S = L7 + A7 - Q7 in {-3..2, 2^32-4..2^32+2,
+    2^33-5..2^33-2} with the low 224 bits at their extremes, plus 10^6 random triples.  The exact path
+    fires for ~2^-29 of the candidates (about 48 times per second per GPU in production), i.e.
+    essentially never in the other tests."""
+    rnd = random.Random(12)
+    Bq = 1 << 32
+    lows = [0, 1, 2**224 - 1, 2**224 - 2, 2**223, 2**64 - 1, 2**64, 977, 2**32 + 977, 2**224 - 2**32 - 977]
+    Ls, As, Qs, want_exact = [], [], [], []
+    for S in [-3, -2, -1, 0, 1, 2, Bq - 4, Bq - 3, Bq - 2, Bq - 1, Bq, Bq + 1, Bq + 2, 2 * Bq - 5, 2 * Bq - 4, 2 * Bq - 3, 2 * Bq - 2]:
+        made = 0
+        while made < 400:
+            l7, q7 = rnd.randrange(Bq), rnd.randrange(Bq)
+            if S >= 2 * Bq - 5:
+                l7, q7 = Bq - 1 - rnd.randrange(3), rnd.randrange(3)
+            a7 = S - l7 + q7
+            if not 0 <= a7 < Bq:
+                continue
+            lo = [rnd.choice(lows + [rnd.getrandbits(224)] * 4) for _ in range(3)]
+            L = (l7 << 224) | lo[0]; A = (a7 << 224) | lo[1]; Q = (q7 << 224) | lo[2]
+            if A < P and Q < P:
+                Ls.append(L); As.append(A); Qs.append(Q); made += 1
+                want_exact.append(S in (-1, 0, Bq - 2, Bq - 1, Bq, 2 * Bq - 3, 2 * Bq - 2))
+    nb = len(Ls)
+    assert nb >= 6000 and sum(want_exact) >= 2400
+    rs = np.random.RandomState(5)
+    nrand = 1_000_000
+    raw = rs.randint(0, 2**32, size=(3, nrand, 8), dtype=np.uint64).astype(np.uint32)
+    raw[1:, :, 7] &= 0x7FFFFFFF                                       # A, Q < 2^255 < p
+    import numpy as _np
+    def ints(a):
+        return [int.from_bytes(row.tobytes(), "little") for row in a]
+    Lr, Ar, Qr = ints(raw[0]), ints(raw[1]), ints(raw[2])
+    keys, ex = pkg.native.debug_key(Ls + Lr, As + Ar, Qs + Qr)
+    assert [bool(x) for x in ex[:nb]] == want_exact
+    want = [((l + a - q) % P) & M64 for l, a, q in zip(Ls + Lr, As + Ar, Qs + Qr)]
+    assert keys.tolist() == want
+    assert int(ex[nb:].sum()) <= 8                                    # ~2^-29 each: the random part stays on the fast path
+
+
 # ------------------------------------------------------------------ table layouts
 @pytest.mark.parametrize("w,htsz", [(50000, 14), (50000, 9), (3000, 12), (1, 1), (200000, 13)])
 def test_probe_layout_vs_oracle(pkg, orc, w, htsz):

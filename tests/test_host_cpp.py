@@ -56,6 +56,22 @@ def test_unsafe_warning(exe):
     assert rc == 0 and "UNSAFE" in out                                                  # README.md:19-24 of the reference
 
 
+@pytest.mark.parametrize("cnt,running,w,job,total,rates", [(0x1a2b3c, 2, 1 << 30, 3725, 90061, [27000000000, 26500000000]),
+                                                          (1, 1, 4194304, 0, 2, [0]), (0xfff00000000000001, 8, 3037000499, 59, 3600, [25 * 10**9] * 8)])
+def test_status_line_is_the_reference_format_in_both_hosts(exe, cnt, running, w, job, total, rates):
+    """1_9_7File.pb:5135: "Cnt:"+cnt$+" ["+Str(isruning)+"]"+"[ "+perf$+"] = "+Str(totalhash/#MB)+" MKeys/s x2^"+StrD(wald,1)+"=2^"
+    +StrD(hashd+wald,2)+" Jt:"+hh:ii:ss+" Tt:"+hh:ii:ss, perf$ = every GPU's rate / 2^20 followed by a blank."""
+    import math
+    rc, out = run(exe, ["-statusline", ",".join([format(cnt, "x"), str(running), str(w), str(job), str(total)] + [str(r) for r in rates])])
+    mine = b.cli.format_status(cnt, running, rates, w, job, total)
+    assert rc == 0 and out.strip("\n") == mine
+    tot = sum(rates)
+    hms = lambda t: "%02d:%02d:%02d" % (t // 3600 % 24, t // 60 % 60, t % 60)       # noqa: E731
+    want = ("Cnt:" + format(cnt, "x") + " [" + str(running) + "]" + "[ " + "".join(str(r >> 20) + " " for r in rates) + "] = " + str(tot >> 20)
+            + " MKeys/s x2^" + "%.1f" % math.log2(2 * w) + "=2^" + "%.2f" % ((math.log2(tot) if tot else 0) + math.log2(2 * w)) + " Jt:" + hms(job) + " Tt:" + hms(total))
+    assert mine == want
+
+
 # ------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 def test_cpp_host_config0_puzzle40_and_table_files(exe, tmp_path):
