@@ -30,6 +30,7 @@ struct bsgs_ctx {
     uint32_t* d_verdict = nullptr;   // per record: payload j / accepted / rejected (device-side verification)
     uint32_t* h_verdict = nullptr;
     bool verify = false;
+    bool force_exact = false;        // tests: every candidate key through the out-of-line exact path
     gs::WinParams last_wp;           // window constants of the launch whose records are being collected
     uint32_t hit_cap = 1u << 16;
     uint32_t* h_hits = nullptr;      // pinned mirror
@@ -122,6 +123,7 @@ extern "C" void bsgs_destroy(bsgs_ctx* ctx) {
 extern "C" int bsgs_set_option(bsgs_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return BSGS_E_ARG;
     if (!strcmp(name, "verify")) { ctx->verify = value != 0; return BSGS_OK; }      // may be toggled at any time
+    if (!strcmp(name, "force_exact")) { ctx->force_exact = value != 0; return BSGS_OK; }
     if (ctx->d_gx || ctx->d_buckets) return BSGS_E_STATE;       // geometry is baked into the layouts
     if (!strcmp(name, "blocks_per_sm")) { if (value < 1 || value > 3) return BSGS_E_ARG; ctx->blocks_per_sm = (uint32_t)value; compute_geometry(ctx); return BSGS_OK; }
     if (!strcmp(name, "block")) {                               // threads per CTA: 256 (x blocks_per_sm) or 320 (x 2)
@@ -477,6 +479,7 @@ static gs::Tables make_tables(const bsgs_ctx* c) {
     tb.csr_off = (const uint32_t*)c->d_ht; tb.csr_tags = tb.csr_off + c->H + 1;
     tb.hit_count = c->d_hits; tb.hits = c->d_hits + 4; tb.hit_cap = c->hit_cap;
     tb.NT = c->NT; tb.PP = c->PP; tb.N = (uint32_t)c->N; tb.mask = (uint32_t)(c->H - 1);
+    tb.exact_thr = c->force_exact ? 0u : FP_KEY_THR;
     tb.keys_out = nullptr; tb.nkeys = 0;
     return tb;
 }
@@ -499,7 +502,11 @@ static cudaError_t launch_k(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
 }
 static cudaError_t launch_any(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
     if (nwin < 1 || nwin > BSGS_MAX_WINDOWS) return cudaErrorInvalidValue;
+#if !GS_STAGE                                                                           // (the staging slots of 320 threads exceed the static shared-memory limit)
     if (c->block == 320) return launch_k<320, 2>(c, nwin, pxy);                        // 5 warps per scheduler, 96 registers
+#else
+    if (c->block == 320) return cudaErrorInvalidValue;
+#endif
     switch (c->blocks_per_sm) {
         case 1: case 2: return launch_k<256, 2>(c, nwin, pxy);
         case 3: return launch_k<256, 3>(c, nwin, pxy);
@@ -673,21 +680,23 @@ extern "C" int bsgs_debug_field(int device, int op, const uint32_t* a, const uin
     return BSGS_OK;
 }
 
-// the hot loop's key extraction on arbitrary (L, A, Q) triples: keys[i] = low 64 bits of canonical
-// (L + A - Q) mod p, exact[i] = 1 when the out-of-line exact path ran
-extern "C" int bsgs_debug_key(int device, const uint32_t* L, const uint32_t* A, const uint32_t* Q, uint64_t* keys, uint8_t* exact, uint32_t n) {
-    if (!L || !A || !Q || !keys || !exact || !n) return BSGS_E_ARG;
+// the hot loop's key extraction: keys[i] = low 64 bits of canonical (in[i]^2 + A[i] - Q[i]) mod p (mode 0, in[i] =
+// lambda, 8 limbs) or of (in[i] + A[i] - Q[i]) mod p (mode 1, in[i] = an arbitrary 512-bit value, 16 limbs);
+// exact[i] = 1 when the classification asked for the out-of-line exact path; force != 0 sends everything there
+extern "C" int bsgs_debug_key(int device, int mode, const uint32_t* in, const uint32_t* A, const uint32_t* Q, uint64_t* keys, uint8_t* exact, uint32_t n, int force) {
+    if (!in || !A || !Q || !keys || !exact || !n || mode < 0 || mode > 1) return BSGS_E_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return BSGS_E_CUDA;
     uint32_t *dl = nullptr, *da = nullptr, *dq = nullptr; uint64_t* dk = nullptr; uint8_t* de = nullptr; size_t bytes = (size_t)n * 32;
-    cudaError_t e = cudaMalloc(&dl, bytes);
+    const size_t inbytes = bytes * (mode ? 2 : 1);
+    cudaError_t e = cudaMalloc(&dl, inbytes);
     if (e == cudaSuccess) e = cudaMalloc(&da, bytes);
     if (e == cudaSuccess) e = cudaMalloc(&dq, bytes);
     if (e == cudaSuccess) e = cudaMalloc(&dk, (size_t)n * 8);
     if (e == cudaSuccess) e = cudaMalloc(&de, n);
-    if (e == cudaSuccess) e = cudaMemcpy(dl, L, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dl, in, inbytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(da, A, bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(dq, Q, bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) { gs::k_debug_key<<<(n + 127) / 128, 128>>>(dl, da, dq, dk, de, n); e = cudaGetLastError(); }
+    if (e == cudaSuccess) { gs::k_debug_key<<<(n + 127) / 128, 128>>>(mode, dl, da, dq, dk, de, n, force ? 0u : FP_KEY_THR); e = cudaGetLastError(); }
     if (e == cudaSuccess) e = cudaMemcpy(keys, dk, (size_t)n * 8, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(exact, de, n, cudaMemcpyDeviceToHost);
     cudaFree(dl); cudaFree(da); cudaFree(dq); cudaFree(dk); cudaFree(de);

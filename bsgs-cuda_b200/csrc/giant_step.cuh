@@ -45,6 +45,14 @@
 #define GS_ABLATE 0
 #endif
 
+// GS_STAGE = 1: the fingerprint sector of every key is copied asynchronously (cp.async, 2 x 16 bytes, L2 only)
+// into a per-thread slot of shared memory at the moment the key is known; the drain reads shared memory
+// instead of issuing the 256-bit global load itself.  Needs GS_RING <= 4 at three 256-thread CTAs per SM
+// (32 bytes x ring x threads of shared memory).  0: the drain loads the sectors (bursts of GS_GROUP).
+#ifndef GS_STAGE
+#define GS_STAGE 0
+#endif
+
 namespace gs {
 
 constexpr int kMaxW = 16;
@@ -80,6 +88,7 @@ struct Tables {
     uint32_t hit_cap;
     uint32_t NT, PP, N;       // threads in the grid, points per thread, giants
     uint32_t mask;            // H - 1
+    uint32_t exact_thr;       // acceptance threshold of fp::fe_key_from_wide: FP_KEY_THR; 0 forces the exact path (tests)
     uint64_t* keys_out;       // emit mode: keys_out[m - 1] = low 64 bits of X(m*G), m <= nkeys
     uint64_t nkeys;
 };
@@ -173,6 +182,13 @@ __global__ void k_build_fp_sectors(const uint32_t* __restrict__ off, const uint3
 
 struct FpSector {
     uint4 a, b;
+    // asynchronous copy of bucket h's sector into this thread's staging slot (two uint4 words BLOCK apart)
+    static __device__ __forceinline__ void stage(const Tables& tb, uint32_t h, uint4* slot, int stride) {
+        const uint4* p = reinterpret_cast<const uint4*>(tb.buckets) + 2ull * h;
+        const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(slot), d1 = (uint32_t)__cvta_generic_to_shared(slot + stride);
+        asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d0), "l"(p) : "memory");
+        asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d1), "l"(p + 1) : "memory");
+    }
     __device__ __forceinline__ void load(const Tables& tb, uint32_t h) {
         const uint4* p = reinterpret_cast<const uint4*>(tb.buckets) + 2ull * h;
         // One random 32-byte sector, never reused: a single 256-bit load (LDG.E.256) kept out of L1,
@@ -214,16 +230,26 @@ __device__ __noinline__ uint64_t key_exact(Fe l2, Fe npx, Fe qx) {
     return fp::fe_add_low64_canon(l2.v, u);
 }
 
-// The key of one candidate as the hot loop computes it: low 64 bits of canonical l2 + npx - qx, from
-// the low 64 bits and the top limbs (fp::fe_key_low64) with the out-of-line exact path for the few
-// top-limb patterns that does not decide.  `npx` points at the eight limbs of p - Px (shared memory in
-// the kernel).  k_debug_key runs exactly this function on arbitrary inputs (tests: the exact path
-// fires about 48 times per second per GPU in production and essentially never at test sizes).
-__device__ __forceinline__ uint64_t candidate_key(const Fe& l2, uint64_t t_lo, int64_t t7, const uint32_t* npx, const Fe& qx, bool* took_exact = nullptr) {
+// exact, slow: the key from lambda itself (full squaring with reduction, then the exact extraction)
+__device__ __noinline__ uint64_t key_exact_sqr(Fe lam, Fe npx, Fe qx) {
+    Fe l2;
+    fp::fe_sqr(l2.v, lam.v);
+    uint32_t u[8];
+    fp::fe_sub_canon(u, npx.v, qx.v);
+    return fp::fe_add_low64_canon(l2.v, u);
+}
+// The key of one candidate as the hot loop computes it: low 64 bits of canonical lambda^2 + npx - qx.  The
+// square is taken WITHOUT reduction and the key read off its low 64 bits and the limbs of weight >= 2^224
+// (fp::fe_key_from_wide); the few patterns that does not decide (2^-29 of the candidates, about 100 per second
+// per GPU in production, essentially never at test sizes) go through the out-of-line exact path.  `npx`
+// points at the eight limbs of p - Px (shared memory in the kernel).  The option `force_exact` (thr = 0)
+// sends every candidate through the exact path, so that the whole parity suite can exercise it.
+__device__ __forceinline__ uint64_t candidate_key(const Fe& lam, uint64_t t_lo, int64_t t7, const uint32_t* npx, const Fe& qx, uint32_t thr) {
+    uint32_t v[16];
+    fp::fe_sqr_wide(v, lam.v);
     bool exact_needed;
-    uint64_t key = fp::fe_key_low64(l2.v, t_lo, t7, exact_needed);
-    if (exact_needed) key = key_exact(l2, lds_fe(npx), qx);
-    if (took_exact) *took_exact = exact_needed;
+    uint64_t key = fp::fe_key_from_wide(v, t_lo, t7, thr, exact_needed);
+    if (exact_needed) key = key_exact_sqr(lam, lds_fe(npx), qx);
     return key;
 }
 
@@ -258,6 +284,10 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParams wp, int W) {
     __shared__ __align__(16) uint32_t s_win[kMaxW * 32];
     __shared__ uint64_t s_ring[MODE == 0 ? kRing * BLOCK : 1];
+#if GS_STAGE
+    __shared__ uint4 s_sec[MODE == 0 ? kRing * 2 * BLOCK : 1];     // [slot][half][thread]
+    uint4* const sec_slot = s_sec + threadIdx.x;
+#endif
     const uint32_t t = blockIdx.x * BLOCK + threadIdx.x;
     const uint32_t NT = tb.NT;
     const int PP = (int)tb.PP;
@@ -348,20 +378,24 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
         { Fe x; fp::fe_mul(x.v, inv.v, d.v); inv = x; }            // 1 / (d_0 ... d_{ci-1})
         uint64_t* rp = ring + fill * BLOCK;
         if (!eq) {
-            // X = lambda^2 + (p - Px) - Qx is never formed: its low 64 bits follow from the low 64 bits and
-            // the top limbs of the three terms (fp::fe_key_low64); the part common to both candidates:
+            // X = lambda^2 + (p - Px) - Qx is never formed, lambda^2 not even reduced: the low 64 bits of X follow
+            // from a few limbs of the 512-bit square and of the other two terms (fp::fe_key_from_wide); the part
+            // common to both candidates:
             const uint64_t t_lo = *reinterpret_cast<const uint64_t*>(sw + 16) - (((uint64_t)qx.v[1] << 32) | qx.v[0]);
             const int64_t t7 = (int64_t)sw[23] - (int64_t)qx.v[7];
 #pragma unroll
             for (int side = 0; side < 2; side++) {                  // side 0: P - Q (code 2), slope (Py + Qy)/d ; side 1: P + Q (code 1), slope (Py - Qy)/d
-                Fe py = lds_fe(sw + 8), sum, lam, l2;
+                Fe py = lds_fe(sw + 8), sum, lam;
                 if (side == 0) fp::fe_add_lazy(sum.v, py.v, qy.v);
                 else fp::fe_sub_canon(sum.v, py.v, qy.v);
                 fp::fe_mul(lam.v, sum.v, invd.v);
-                fp::fe_sqr(l2.v, lam.v);
-                const uint64_t key = candidate_key(l2, t_lo, t7, sw + 16, qx);
-                if (MODE == 0) rp[side * BLOCK] = key;
-                else if (kidx < tb.N) {                             // multiplier C - (i+1) (side 0) or C + (i+1) (side 1)
+                const uint64_t key = candidate_key(lam, t_lo, t7, sw + 16, qx, tb.exact_thr);
+                if (MODE == 0) {
+                    rp[side * BLOCK] = key;
+#if GS_STAGE
+                    FpSector::stage(tb, (uint32_t)key & tb.mask, sec_slot + (fill + side) * 2 * BLOCK, BLOCK);
+#endif
+                } else if (kidx < tb.N) {                             // multiplier C - (i+1) (side 0) or C + (i+1) (side 1)
                     const uint64_t i1 = (uint64_t)kidx + 1, c = wp.center[(sw - s_win) >> 5];
                     const uint64_t m = side == 0 ? c - i1 : c + i1;
                     if (m <= tb.nkeys) tb.keys_out[m - 1] = key;
@@ -370,7 +404,12 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
         } else {
             Fe px = lds_fe(sw);
             const uint64_t key = double_x_low64_v(px, invd);        // X(2P)  (code 4); cannot occur in emit mode
-            if (MODE == 0) rp[0] = key;
+            if (MODE == 0) {
+                rp[0] = key;
+#if GS_STAGE
+                FpSector::stage(tb, (uint32_t)key & tb.mask, sec_slot + fill * 2 * BLOCK, BLOCK);
+#endif
+            }
             special = true;
         }
         if (MODE == 0) {
@@ -380,13 +419,20 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
                 // drain: slot 2j / 2j+1 = minus / plus key of chain index ci_first - j
                 const int ci_first = ci + (fill >> 1) - 1;
                 if (ci == 0) special = true;                        // the last burst may end inside a group of four
+#if GS_STAGE
+                asm volatile("cp.async.wait_all;" ::: "memory");     // this thread's own copies; nobody else reads its slots
+#endif
 #pragma unroll 1
                 for (int s0 = 0; s0 < fill; s0 += kGroup) {
                     FpSector sec[kGroup]; uint64_t key[kGroup];
 #pragma unroll
                     for (int j = 0; j < kGroup; j++) {
                         key[j] = ring[(s0 + j) * BLOCK];
+#if GS_STAGE
+                        sec[j].a = sec_slot[(s0 + j) * 2 * BLOCK]; sec[j].b = sec_slot[((s0 + j) * 2 + 1) * BLOCK];
+#else
                         sec[j].load(tb, (uint32_t)key[j] & tb.mask);
+#endif
                     }
                     uint32_t need = special ? (1u << kGroup) - 1u : 0u;
 #pragma unroll
@@ -481,20 +527,39 @@ __global__ void k_debug_field(int op, const uint32_t* a, const uint32_t* b, uint
     for (int j = 0; j < 8; j++) r[8 * i + j] = z[j];
 }
 
-// diagnostics: the hot loop's key extraction (candidate_key: fe_key_low64 + key_exact) on arbitrary
-// triples (L lazy, A and Q canonical), formed exactly as PASS 2 forms them
-__global__ void k_debug_key(const uint32_t* L, const uint32_t* A, const uint32_t* Q, uint64_t* keys, uint8_t* exact, uint32_t n) {
+// diagnostics: the hot loop's key extraction on arbitrary inputs, formed exactly as PASS 2 forms them.
+// mode 0: in[i] = lambda (8 limbs): candidate_key itself (square, classification, exact path via lambda).
+// mode 1: in[i] = an arbitrary 512-bit v (16 limbs) in place of lambda^2: the same classification and fast
+//         path (fp::fe_key_from_wide); the exact path reduces v and runs the same exact extraction.
+__global__ void k_debug_key(int mode, const uint32_t* in, const uint32_t* A, const uint32_t* Q, uint64_t* keys, uint8_t* exact, uint32_t n, uint32_t thr) {
     __shared__ __align__(16) uint32_t s_a[128 * 8];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Fe l2, qx;
+    Fe qx;
     uint32_t* a = s_a + threadIdx.x * 8;
 #pragma unroll
-    for (int j = 0; j < 8; j++) { l2.v[j] = L[8 * i + j]; qx.v[j] = Q[8 * i + j]; a[j] = A[8 * i + j]; }
+    for (int j = 0; j < 8; j++) { qx.v[j] = Q[8 * i + j]; a[j] = A[8 * i + j]; }
     const uint64_t t_lo = *reinterpret_cast<const uint64_t*>(a) - (((uint64_t)qx.v[1] << 32) | qx.v[0]);
     const int64_t t7 = (int64_t)a[7] - (int64_t)qx.v[7];
+    uint32_t v[16];
+    Fe lam;
+    if (mode == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) lam.v[j] = in[8 * i + j];
+        fp::fe_sqr_wide(v, lam.v);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = in[16 * i + j];
+    }
     bool ex;
-    keys[i] = candidate_key(l2, t_lo, t7, a, qx, &ex);
+    uint64_t key = fp::fe_key_from_wide(v, t_lo, t7, thr, ex);
+    if (mode == 0) key = candidate_key(lam, t_lo, t7, a, qx, thr);
+    else if (ex) {
+        Fe l2; fp::reduce512(l2.v, v);
+        uint32_t u[8]; fp::fe_sub_canon(u, a, qx.v);
+        key = fp::fe_add_low64_canon(l2.v, u);
+    }
+    keys[i] = key;
     exact[i] = ex ? 1 : 0;
 }
 

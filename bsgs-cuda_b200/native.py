@@ -80,7 +80,7 @@ def load():
     L.bsgs_get_info.argtypes = [vp, C.POINTER(Info)]
     L.bsgs_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.bsgs_debug_field.argtypes = [C.c_int, C.c_int, vp, vp, vp, u32]
-    L.bsgs_debug_key.argtypes = [C.c_int, vp, vp, vp, vp, vp, u32]
+    L.bsgs_debug_key.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, u32, C.c_int]
     L.bsgs_bcast_ht.argtypes = [C.POINTER(vp), C.c_int]
     L.bsgs_device_count.argtypes = [C.POINTER(C.c_int)]
     L.bsgs_device_query.argtypes = [C.c_int, C.POINTER(DevInfo)]
@@ -132,13 +132,17 @@ def _limbs(vals):
     return np.ascontiguousarray(a.reshape(len(vals), 8))
 
 
-def debug_key(Ls, As, Qs, device=0):
-    """The kernel's key extraction (candidate_key in giant_step.cuh) on triples (L, A, Q): returns
-    (keys, exact_flags) as numpy arrays."""
-    n = len(Ls)
-    L_, A_, Q_ = _limbs(Ls), _limbs(As), _limbs(Qs)
+def debug_key(ins, As, Qs, wide=False, force=False, device=0):
+    """The kernel's key extraction (candidate_key in giant_step.cuh): ins = lambdas (wide=False) or arbitrary
+    512-bit values standing for lambda^2 (wide=True); returns (keys, exact_flags) as numpy arrays."""
+    n = len(ins)
+    if wide:
+        I_ = np.ascontiguousarray(np.frombuffer(b"".join(int(x).to_bytes(64, "little") for x in ins), dtype=np.uint32).reshape(n, 16))
+    else:
+        I_ = _limbs(ins)
+    A_, Q_ = _limbs(As), _limbs(Qs)
     keys = np.zeros(n, dtype=np.uint64); ex = np.zeros(n, dtype=np.uint8)
-    rc = load().bsgs_debug_key(device, L_.ctypes.data, A_.ctypes.data, Q_.ctypes.data, keys.ctypes.data, ex.ctypes.data, n)
+    rc = load().bsgs_debug_key(device, 1 if wide else 0, I_.ctypes.data, A_.ctypes.data, Q_.ctypes.data, keys.ctypes.data, ex.ctypes.data, n, 1 if force else 0)
     if rc:
         raise BsgsError(rc, "bsgs_debug_key")
     return keys, ex

@@ -155,11 +155,13 @@ int  bsgs_set_option(bsgs_ctx *ctx, const char *name, int64_t value);
  * (op: 0 mul, 1 sqr, 2 inv, 3 sub(canonical), 4 add(lazy), 5 canonicalise, 6 low64 of canonical
  * (a+b), 7 low64 of X(2P) given (Px, 1/(2Py))).  Used by the parity tests of the limb arithmetic. */
 int  bsgs_debug_field(int device, int op, const uint32_t *a, const uint32_t *b, uint32_t *r, uint32_t n);
-/* the giant-step kernel's own key extraction (the inlined fast classification on the low 64 bits and
- * the top limbs, plus the out-of-line exact path it falls back to for ~2^-29 of the candidates) run
- * on n triples: keys[i] = low 64 bits of canonical (L[i] + A[i] - Q[i]) mod p with L any 256-bit
- * value and A, Q < p; exact[i] = 1 when the exact path ran.  Parity test of that rare path. */
-int  bsgs_debug_key(int device, const uint32_t *L, const uint32_t *A, const uint32_t *Q, uint64_t *keys, uint8_t *exact, uint32_t n);
+/* the giant-step kernel's own key extraction (the square of lambda taken without reduction, the key read
+ * off its low 64 bits and its limbs of weight >= 2^224, plus the out-of-line exact path it falls back to for
+ * ~2^-29 of the candidates) run on n inputs: keys[i] = low 64 bits of canonical (in[i]^2 + A[i] - Q[i]) mod p for
+ * mode 0 (in[i] = lambda, 8 limbs, any 256-bit value) or of (in[i] + A[i] - Q[i]) mod p for mode 1 (in[i] = an
+ * arbitrary 512-bit value in place of the square, 16 limbs); A, Q < p.  exact[i] = 1 when the classification
+ * asked for the exact path; force != 0 sends every input there.  Parity test of that rare path. */
+int  bsgs_debug_key(int device, int mode, const uint32_t *in, const uint32_t *A, const uint32_t *Q, uint64_t *keys, uint8_t *exact, uint32_t n, int force);
 
 #ifdef __cplusplus
 }

@@ -58,44 +58,58 @@ def test_low64_slow_path_on_device(pkg):
 
 
 def test_hot_loop_key_extraction_on_device_incl_the_exact_path(pkg):
-    """candidate_key (fe_key_low64 + out-of-line key_exact, giant_step.cuh) ON THE DEVICE, as PASS 2 calls
-    it: boundary cases of the top-limb classification S = L7 + A7 - Q7 in {-3..2, 2^32-4..2^32+2,
-    2^33-5..2^33-2} with the low 224 bits at their extremes, plus 10^6 random triples.  The exact path
-    fires for ~2^-29 of the candidates (about 48 times per second per GPU in production), i.e.
-    essentially never in the other tests."""
+    """candidate_key (giant_step.cuh) ON THE DEVICE, as PASS 2 calls it: lambda is squared without reduction and
+    the key read off a few limbs of the 512-bit square (fp::fe_key_from_wide); ~2^-29 of the candidates (about
+    100 per second per GPU in production, essentially never in the other tests) take the out-of-line exact path.
+    (a) 512-bit values crafted around every boundary of the classification word s (with the part below 2^224
+    at both extremes of its carry) in place of the square; (b) 10^6 random lambdas through the real thing;
+    (c) the same lambdas with the exact path forced."""
+    from tests.test_fp_hostemu import _wide_case_with_s
     rnd = random.Random(12)
     Bq = 1 << 32
-    lows = [0, 1, 2**224 - 1, 2**224 - 2, 2**223, 2**64 - 1, 2**64, 977, 2**32 + 977, 2**224 - 2**32 - 977]
-    Ls, As, Qs, want_exact = [], [], [], []
-    for S in [-3, -2, -1, 0, 1, 2, Bq - 4, Bq - 3, Bq - 2, Bq - 1, Bq, Bq + 1, Bq + 2, 2 * Bq - 5, 2 * Bq - 4, 2 * Bq - 3, 2 * Bq - 2]:
-        made = 0
-        while made < 400:
-            l7, q7 = rnd.randrange(Bq), rnd.randrange(Bq)
-            if S >= 2 * Bq - 5:
-                l7, q7 = Bq - 1 - rnd.randrange(3), rnd.randrange(3)
-            a7 = S - l7 + q7
-            if not 0 <= a7 < Bq:
-                continue
-            lo = [rnd.choice(lows + [rnd.getrandbits(224)] * 4) for _ in range(3)]
-            L = (l7 << 224) | lo[0]; A = (a7 << 224) | lo[1]; Q = (q7 << 224) | lo[2]
-            if A < P and Q < P:
-                Ls.append(L); As.append(A); Qs.append(Q); made += 1
-                want_exact.append(S in (-1, 0, Bq - 2, Bq - 1, Bq, 2 * Bq - 3, 2 * Bq - 2))
-    nb = len(Ls)
-    assert nb >= 6000 and sum(want_exact) >= 2400
+    vs, As, Qs, want_exact = [], [], [], []
+    for s in [0, 1, 2, 3, 4, 5, 6, 7, Bq - 9, Bq - 8, Bq - 7, Bq - 6, Bq - 5, Bq - 4, Bq - 3, Bq - 2, Bq - 1]:
+        for extreme in ("max", "min", "rnd"):
+            for _ in range(120):
+                v, A, Q = _wide_case_with_s(rnd, s, extreme)
+                vs.append(v); As.append(A); Qs.append(Q); want_exact.append(not 2 <= s <= Bq - 6)
+    for _ in range(2000):
+        vs.append(rnd.getrandbits(512)); As.append(rnd.randrange(P)); Qs.append(rnd.randrange(P)); want_exact.append(None)
+    keys, ex = pkg.native.debug_key(vs, As, Qs, wide=True)
+    assert keys.tolist() == [((v + a - q) % P) & M64 for v, a, q in zip(vs, As, Qs)]
+    assert all(w is None or bool(e) == w for e, w in zip(ex, want_exact)) and sum(1 for w in want_exact if w) >= 2500
     rs = np.random.RandomState(5)
     nrand = 1_000_000
     raw = rs.randint(0, 2**32, size=(3, nrand, 8), dtype=np.uint64).astype(np.uint32)
     raw[1:, :, 7] &= 0x7FFFFFFF                                       # A, Q < 2^255 < p
-    import numpy as _np
     def ints(a):
         return [int.from_bytes(row.tobytes(), "little") for row in a]
     Lr, Ar, Qr = ints(raw[0]), ints(raw[1]), ints(raw[2])
-    keys, ex = pkg.native.debug_key(Ls + Lr, As + Ar, Qs + Qr)
-    assert [bool(x) for x in ex[:nb]] == want_exact
-    want = [((l + a - q) % P) & M64 for l, a, q in zip(Ls + Lr, As + Ar, Qs + Qr)]
+    want = [((l * l + a - q) % P) & M64 for l, a, q in zip(Lr, Ar, Qr)]
+    keys, ex = pkg.native.debug_key(Lr, Ar, Qr)
     assert keys.tolist() == want
-    assert int(ex[nb:].sum()) <= 8                                    # ~2^-29 each: the random part stays on the fast path
+    assert int(ex.sum()) <= 8                                         # ~2^-29 each: random inputs stay on the fast path
+    n2 = 100_000
+    edge = [0, 1, P - 1, P, 2**256 - 1, 2**255, 2**128]
+    keys, ex = pkg.native.debug_key(edge + Lr[:n2], [P - 1] * len(edge) + Ar[:n2], [0] * len(edge) + Qr[:n2], force=True)
+    assert keys.tolist() == [((l * l + P - 1) % P) & M64 for l in edge] + want[:n2]
+    assert int(ex.sum()) >= len(keys) - 4                             # forced: all but s == 2
+
+
+def test_whole_launch_with_the_exact_key_path_forced(pkg, orc):
+    """Option force_exact: every candidate of a launch goes through the out-of-line exact path of the hot loop
+    (key_exact_sqr); the records must not change."""
+    T, B, p, w, htsz = 64, 8, 16, 20000, 11
+    Ppt, plant, cpu, gpu, g2 = build_case(orc, T, B, p, w, htsz, seed=777)
+    with pkg.Engine(T, B, p, w, htsz) as e:
+        e.upload_giants(g2); e.upload_ht(gpu)
+        fast = norm_hits(e.step(Ppt))
+        e._ck(e.L.bsgs_set_option(e.h, b"force_exact", 1), "force_exact")
+        slow = norm_hits(e.step(Ppt))
+        multi = sorted((wi, c, i) for c, i, wi in e.step_multi([Ppt, pyec.add(Ppt, pyec.G), Ppt]))
+        e._ck(e.L.bsgs_set_option(e.h, b"force_exact", 0), "force_exact")
+        assert fast == slow == norm_hits(orc.launch(g2, T, B, p, gpu, htsz, Ppt)) and set(plant) <= set(slow)
+        assert [(c, i) for wi, c, i in multi if wi == 0] == [(c, i) for wi, c, i in multi if wi == 2] == fast
 
 
 # ------------------------------------------------------------------ table layouts
