@@ -231,8 +231,8 @@ def main(argv=None, out=sys.stdout) -> int:
                 nwin = s.windows_needed(o["pke"])
                 done = 0
                 while done < nwin and not state["stop"]:
-                    chunk = min(nwin - done, 16)
-                    hits, d = e.run(s.window_point(done), s.D, chunk, batch=chunk, stop_after_hits=1)
+                    chunk = min(nwin - done, 128)                  # 8 launches of 16 windows, two in flight inside bsgs_run
+                    hits, d = e.run(s.window_point(done), s.D, chunk, batch=min(chunk, 16), stop_after_hits=1)
                     for (code, idx, win), payload in zip(hits, list(e.payloads)):
                         if payload != 0xFFFFFFFF:
                             k = s.check_verified(code, idx, done + win, payload)

@@ -31,6 +31,7 @@ struct bsgs_ctx {
     uint32_t* h_verdict = nullptr;
     bool verify = false;
     bool force_exact = false;        // tests: every candidate key through the out-of-line exact path
+    uint64_t* d_trace = nullptr;     // diagnostics: per-warp SM id and timestamps of the last launch (option "trace")
     gs::WinParams last_wp;           // window constants of the launch whose records are being collected
     uint32_t hit_cap = 1u << 16;
     uint32_t* h_hits = nullptr;      // pinned mirror
@@ -39,7 +40,23 @@ struct bsgs_ctx {
     unsigned long long overfull = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    // Second launch lane (bsgs_run / bsgs_time_launches): its own stream, chain, record buffers.  Launches alternate
+    // between the lanes so that two are in flight: the warps of a launch do not finish together (the hardware
+    // arbiter favours some warps: the first warp of an SM is done after 58 % of the kernel), and
+    // the CTAs of the next launch take the slots they leave instead of the SM draining at every launch boundary.
+    bool overlap = true;
+    cudaStream_t stream2 = nullptr;
+    uint4* d_chain2 = nullptr;
+    uint32_t *d_hits2 = nullptr, *h_hits2 = nullptr, *d_verdict2 = nullptr, *h_verdict2 = nullptr;
+    gs::WinParams last_wp2;
+    cudaEvent_t e2 = nullptr;
 };
+
+struct Lane { cudaStream_t st; uint4* chain; uint32_t *d_hits, *h_hits, *d_verdict, *h_verdict; gs::WinParams* wp; };
+static Lane lane_of(bsgs_ctx* c, int i) {
+    if (i == 0) return Lane{c->stream, c->d_chain, c->d_hits, c->h_hits, c->d_verdict, c->h_verdict, &c->last_wp};
+    return Lane{c->stream2, c->d_chain2, c->d_hits2, c->h_hits2, c->d_verdict2, c->h_verdict2, &c->last_wp2};
+}
 
 #define CU(call)                                                         \
     do {                                                                 \
@@ -52,7 +69,8 @@ struct bsgs_ctx {
     } while (0)
 
 static int alloc_giants(bsgs_ctx* ctx);
-static gs::Tables make_tables(const bsgs_ctx* c);
+static int ensure_lane2(bsgs_ctx* ctx);
+static gs::Tables make_tables(const bsgs_ctx* c, int lane = 0);
 static void fill_win(gs::WinConst& wc, const uint8_t* pxy);
 static size_t ht_image_bytes(const bsgs_ctx* c) { return (size_t)c->H * 4 + 4 + (size_t)c->w * 4; }
 
@@ -110,7 +128,12 @@ extern "C" void bsgs_destroy(bsgs_ctx* ctx) {
     cudaSetDevice(ctx->dev);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_g2_stage); cudaFree(ctx->d_gx); cudaFree(ctx->d_gy); cudaFree(ctx->d_chain);
-    cudaFree(ctx->d_ht); cudaFree(ctx->d_buckets); cudaFree(ctx->d_js); cudaFree(ctx->d_hits); cudaFree(ctx->d_scratch); cudaFree(ctx->d_verdict);
+    cudaFree(ctx->d_ht); cudaFree(ctx->d_buckets); cudaFree(ctx->d_js); cudaFree(ctx->d_hits); cudaFree(ctx->d_scratch); cudaFree(ctx->d_verdict); cudaFree(ctx->d_trace);
+    cudaFree(ctx->d_chain2); cudaFree(ctx->d_hits2); cudaFree(ctx->d_verdict2);
+    if (ctx->h_hits2) cudaFreeHost(ctx->h_hits2);
+    if (ctx->h_verdict2) cudaFreeHost(ctx->h_verdict2);
+    if (ctx->e2) cudaEventDestroy(ctx->e2);
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     if (ctx->h_verdict) cudaFreeHost(ctx->h_verdict);
     if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
     if (ctx->e0) cudaEventDestroy(ctx->e0);
@@ -124,6 +147,13 @@ extern "C" int bsgs_set_option(bsgs_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return BSGS_E_ARG;
     if (!strcmp(name, "verify")) { ctx->verify = value != 0; return BSGS_OK; }      // may be toggled at any time
     if (!strcmp(name, "force_exact")) { ctx->force_exact = value != 0; return BSGS_OK; }
+    if (!strcmp(name, "overlap")) { ctx->overlap = value != 0; return BSGS_OK; }    // 0: one launch at a time (bsgs_run, bsgs_time_launches)
+    if (!strcmp(name, "trace")) {                                                  // per-warp timestamps of every following launch
+        CU(cudaSetDevice(ctx->dev));
+        if (value && !ctx->d_trace) CU(cudaMalloc(&ctx->d_trace, (size_t)ctx->NT / 32 * 32));
+        if (!value && ctx->d_trace) { cudaFree(ctx->d_trace); ctx->d_trace = nullptr; }
+        return BSGS_OK;
+    }
     if (ctx->d_gx || ctx->d_buckets) return BSGS_E_STATE;       // geometry is baked into the layouts
     if (!strcmp(name, "blocks_per_sm")) { if (value < 1 || value > 3) return BSGS_E_ARG; ctx->blocks_per_sm = (uint32_t)value; compute_geometry(ctx); return BSGS_OK; }
     if (!strcmp(name, "block")) {                               // threads per CTA: 256 (x blocks_per_sm) or 320 (x 2)
@@ -473,14 +503,15 @@ extern "C" int bsgs_ht_device_image(bsgs_ctx* ctx, void** dev_ptr, size_t* bytes
 }
 
 // ------------------------------------------------------------------------------------------------ hot path
-static gs::Tables make_tables(const bsgs_ctx* c) {
+static gs::Tables make_tables(const bsgs_ctx* c, int lane) {
     gs::Tables tb;
-    tb.gx = c->d_gx; tb.gy = c->d_gy; tb.chain = c->d_chain; tb.buckets = c->d_buckets;
+    tb.gx = c->d_gx; tb.gy = c->d_gy; tb.chain = lane ? c->d_chain2 : c->d_chain; tb.buckets = c->d_buckets;
     tb.csr_off = (const uint32_t*)c->d_ht; tb.csr_tags = tb.csr_off + c->H + 1;
-    tb.hit_count = c->d_hits; tb.hits = c->d_hits + 4; tb.hit_cap = c->hit_cap;
+    tb.hit_count = lane ? c->d_hits2 : c->d_hits; tb.hits = tb.hit_count + 4; tb.hit_cap = c->hit_cap;
     tb.NT = c->NT; tb.PP = c->PP; tb.N = (uint32_t)c->N; tb.mask = (uint32_t)(c->H - 1);
     tb.exact_thr = c->force_exact ? 0u : FP_KEY_THR;
     tb.keys_out = nullptr; tb.nkeys = 0;
+    tb.trace = c->d_trace;
     return tb;
 }
 
@@ -492,59 +523,79 @@ static void fill_win(gs::WinConst& wc, const uint8_t* pxy) {
 }
 
 template <int BLOCK, int MINB>
-static cudaError_t launch_k(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
-    gs::WinParams& wp = c->last_wp;
+static cudaError_t launch_k(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy, int lane) {
+    Lane L = lane_of(c, lane);
+    gs::WinParams& wp = *L.wp;
     memset(&wp, 0, sizeof wp);
     for (uint32_t i = 0; i < nwin; i++) fill_win(wp.win[i], pxy + 64 * i);
-    gs::Tables tb = make_tables(c);
-    gs::k_giant_step<BLOCK, MINB, 0><<<c->grid, BLOCK, 0, c->stream>>>(tb, wp, (int)nwin);
+    gs::Tables tb = make_tables(c, lane);
+    gs::k_giant_step<BLOCK, MINB, 0><<<c->grid, BLOCK, 0, L.st>>>(tb, wp, (int)nwin);
     return cudaGetLastError();
 }
-static cudaError_t launch_any(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy) {
+static cudaError_t launch_any(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy, int lane = 0) {
     if (nwin < 1 || nwin > BSGS_MAX_WINDOWS) return cudaErrorInvalidValue;
 #if !GS_STAGE                                                                           // (the staging slots of 320 threads exceed the static shared-memory limit)
-    if (c->block == 320) return launch_k<320, 2>(c, nwin, pxy);                        // 5 warps per scheduler, 96 registers
+    if (c->block == 320) return launch_k<320, 2>(c, nwin, pxy, lane);                  // 5 warps per scheduler, 96 registers
 #else
     if (c->block == 320) return cudaErrorInvalidValue;
 #endif
     switch (c->blocks_per_sm) {
-        case 1: case 2: return launch_k<256, 2>(c, nwin, pxy);
-        case 3: return launch_k<256, 3>(c, nwin, pxy);
+        case 1: case 2: return launch_k<256, 2>(c, nwin, pxy, lane);
+        case 3: return launch_k<256, 3>(c, nwin, pxy, lane);
         default: return cudaErrorInvalidValue;
     }
 }
 
-// read back counter + records, clear the counter; appends to out[*nhits...] with window offset
-static int collect_hits(bsgs_ctx* ctx, uint32_t window_base, bsgs_hit* out, uint32_t cap, uint32_t* nhits) {
+// second lane, allocated on first use (bsgs_run / bsgs_time_launches with more than one launch)
+static int ensure_lane2(bsgs_ctx* ctx) {
+    if (ctx->stream2) return BSGS_OK;
+    CU(cudaSetDevice(ctx->dev));
+    CU(cudaMalloc(&ctx->d_chain2, ctx->chain_bytes));
+    CU(cudaMalloc(&ctx->d_hits2, 16 + (size_t)ctx->hit_cap * 12));
+    CU(cudaMalloc(&ctx->d_verdict2, (size_t)ctx->hit_cap * 4));
+    CU(cudaMallocHost(&ctx->h_verdict2, (size_t)ctx->hit_cap * 4));
+    CU(cudaMallocHost(&ctx->h_hits2, 16 + (size_t)ctx->hit_cap * 12));
+    CU(cudaEventCreate(&ctx->e2));
+    cudaStream_t st;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU(cudaMemsetAsync(ctx->d_hits2, 0, 16, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->stream2 = st;
+    return BSGS_OK;
+}
+
+// read back counter + records of the launch on `lane`, clear the counter; appends to out[*nhits...] with window offset
+static int collect_hits(bsgs_ctx* ctx, uint32_t window_base, bsgs_hit* out, uint32_t cap, uint32_t* nhits, int lane = 0) {
+    Lane L = lane_of(ctx, lane);
     const uint32_t eager = 64;                                   // one D2H covers the common case
-    CU(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, 16 + eager * 12, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    uint32_t cnt = ctx->h_hits[0];
+    CU(cudaMemcpyAsync(L.h_hits, L.d_hits, 16 + eager * 12, cudaMemcpyDeviceToHost, L.st));
+    CU(cudaStreamSynchronize(L.st));
+    uint32_t cnt = L.h_hits[0];
     if (cnt == 0) return BSGS_OK;
     uint32_t stored = cnt < ctx->hit_cap ? cnt : ctx->hit_cap;
     if (stored > eager) {
-        CU(cudaMemcpyAsync(ctx->h_hits + 4 + eager * 3, ctx->d_hits + 4 + eager * 3, (size_t)(stored - eager) * 12, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(L.h_hits + 4 + eager * 3, L.d_hits + 4 + eager * 3, (size_t)(stored - eager) * 12, cudaMemcpyDeviceToHost, L.st));
     }
     const bool verify = ctx->verify && ctx->d_js;
     if (verify) {                                                // re-examine every record where it was produced
-        gs::Tables tb = make_tables(ctx);
-        vfy::k_verify_hits<<<(stored + 31) / 32, 32, 0, ctx->stream>>>(tb, ctx->last_wp, ctx->d_js, stored, ctx->d_verdict);
+        gs::Tables tb = make_tables(ctx, lane);
+        vfy::k_verify_hits<<<(stored + 31) / 32, 32, 0, L.st>>>(tb, *L.wp, ctx->d_js, stored, L.d_verdict);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(ctx->h_verdict, ctx->d_verdict, (size_t)stored * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(L.h_verdict, L.d_verdict, (size_t)stored * 4, cudaMemcpyDeviceToHost, L.st));
     }
-    CU(cudaMemsetAsync(ctx->d_hits, 0, 4, ctx->stream));         // F197:2500-2504
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemsetAsync(L.d_hits, 0, 4, L.st));                   // F197:2500-2504
+    CU(cudaStreamSynchronize(L.st));
     int rc = cnt > ctx->hit_cap ? BSGS_E_OVERFLOW : BSGS_OK;
     for (uint32_t i = 0; i < stored; i++) {
         uint32_t payload = 0xFFFFFFFFu;
         if (verify) {
-            payload = ctx->h_verdict[i];
+            payload = L.h_verdict[i];
             if (payload == 0xFFFFFFFFu) continue;                // false positive of the 32-bit-tag table: dropped
         }
         uint32_t pos = *nhits;
         if (pos < cap && out) {
-            out[pos].code = ctx->h_hits[4 + 3 * i]; out[pos].idx = ctx->h_hits[4 + 3 * i + 1];
-            out[pos].window = window_base + ctx->h_hits[4 + 3 * i + 2]; out[pos].reserved = payload;
+            out[pos].code = L.h_hits[4 + 3 * i]; out[pos].idx = L.h_hits[4 + 3 * i + 1];
+            out[pos].window = window_base + L.h_hits[4 + 3 * i + 2]; out[pos].reserved = payload;
         } else rc = BSGS_E_OVERFLOW;
         (*nhits)++;
     }
@@ -580,20 +631,36 @@ extern "C" int bsgs_run(bsgs_ctx* ctx, const uint8_t p0xy_le[64], const uint8_t 
     auto fill = [&](uint8_t* buf, uint32_t n) {                 // GetJob (F197:2077-2092), n windows ahead
         for (uint32_t i = 0; i < n; i++) { hec::store_le(buf + 64 * i, P.x); hec::store_le(buf + 64 * i + 32, P.y); hec::pt_add(P, P, D); }
     };
-    uint32_t n = (uint32_t)(nwindows - done < batch ? nwindows - done : batch);
-    if (n) fill(cur, n);
+    const bool two = ctx->overlap && nwindows > batch;             // two launches in flight, alternating lanes
+    if (two) { int r = ensure_lane2(ctx); if (r) return r; }
+    uint32_t n = (uint32_t)(nwindows < batch ? nwindows : batch);
+    uint64_t issued = 0; int lane = 0;
+    if (n) { fill(cur, n); CU(launch_any(ctx, n, cur, 0)); issued = n; }
     while (done < nwindows) {
-        CU(launch_any(ctx, n, cur));
-        // overlap: derive the next batch of base points on the host while the kernel runs
-        uint64_t left = nwindows - done - n;
+        // the next batch: base points derived on the host while the kernel runs; with two lanes it is launched BEFORE
+        // the records of the current one are collected
+        uint64_t left = nwindows - issued;
         uint32_t n2 = (uint32_t)(left < batch ? left : batch);
-        if (n2) fill(nxt, n2);
-        int r2 = collect_hits(ctx, (uint32_t)done, out, cap, nhits);
+        if (n2) {
+            fill(nxt, n2);
+            if (two) { CU(launch_any(ctx, n2, nxt, lane ^ 1)); issued += n2; }
+        }
+        int r2 = collect_hits(ctx, (uint32_t)done, out, cap, nhits, lane);
         done += n;
-        if (r2 && r2 != BSGS_E_OVERFLOW) { rc = r2; break; }
-        if (r2 == BSGS_E_OVERFLOW) rc = r2;
-        if (stop_after_hits && *nhits >= stop_after_hits) break;
-        memcpy(cur, nxt, sizeof cur); n = n2;
+        bool stop = (r2 && r2 != BSGS_E_OVERFLOW) || (stop_after_hits && *nhits >= stop_after_hits);
+        if (r2 == BSGS_E_OVERFLOW) rc = r2; else if (r2) rc = r2;
+        if (stop) {
+            if (two && n2) {                                        // one more launch is already running: its windows count too
+                int r3 = collect_hits(ctx, (uint32_t)done, out, cap, nhits, lane ^ 1);
+                done += n2;
+                if (r3 && rc == BSGS_OK) rc = r3;
+            }
+            break;
+        }
+        if (!n2) break;
+        if (two) lane ^= 1;
+        else { CU(launch_any(ctx, n2, nxt, 0)); issued += n2; }
+        n = n2;
     }
     if (windows_done) *windows_done = done;
     return rc;
@@ -604,12 +671,17 @@ extern "C" int bsgs_time_launches(bsgs_ctx* ctx, uint32_t nwin, const uint8_t* p
     if (!ctx || !pxy_le || !ms || nwin < 1 || nwin > ctx->max_windows || !iters) return BSGS_E_ARG;
     if (!ctx->giants_ready || !ctx->ht_ready) return BSGS_E_STATE;
     CU(cudaSetDevice(ctx->dev));
+    const bool two = ctx->overlap && iters > 1;
+    if (two) { int r = ensure_lane2(ctx); if (r) return r; }
     CU(cudaEventRecord(ctx->e0, ctx->stream));
-    for (uint32_t i = 0; i < iters; i++) CU(launch_any(ctx, nwin, pxy_le + (size_t)i * nwin * 64));
+    if (two) CU(cudaStreamWaitEvent(ctx->stream2, ctx->e0, 0));      // nothing of the timed region starts before e0
+    for (uint32_t i = 0; i < iters; i++) CU(launch_any(ctx, nwin, pxy_le + (size_t)i * nwin * 64, two ? (int)(i & 1) : 0));
+    if (two) { CU(cudaEventRecord(ctx->e2, ctx->stream2)); CU(cudaStreamWaitEvent(ctx->stream, ctx->e2, 0)); }    // e1 after both lanes
     CU(cudaEventRecord(ctx->e1, ctx->stream));
     CU(cudaEventSynchronize(ctx->e1));
     CU(cudaEventElapsedTime(ms, ctx->e0, ctx->e1));
     CU(cudaMemsetAsync(ctx->d_hits, 0, 4, ctx->stream));
+    if (two) { CU(cudaMemsetAsync(ctx->d_hits2, 0, 4, ctx->stream2)); CU(cudaStreamSynchronize(ctx->stream2)); }
     CU(cudaStreamSynchronize(ctx->stream));
     return BSGS_OK;
 }
@@ -701,5 +773,18 @@ extern "C" int bsgs_debug_key(int device, int mode, const uint32_t* in, const ui
     if (e == cudaSuccess) e = cudaMemcpy(exact, de, n, cudaMemcpyDeviceToHost);
     cudaFree(dl); cudaFree(da); cudaFree(dq); cudaFree(dk); cudaFree(de);
     if (e != cudaSuccess) { cudaGetLastError(); return BSGS_E_CUDA; }
+    return BSGS_OK;
+}
+
+// diagnostics: per-warp {SM id, globaltimer ns at kernel start, after pass 1, at the end} of the last launch
+// (option "trace" = 1 before the launch); out holds 4 words per warp, *nwarps warps
+extern "C" int bsgs_debug_trace(bsgs_ctx* ctx, uint64_t* out, uint32_t cap_warps, uint32_t* nwarps) {
+    if (!ctx || !out || !nwarps) return BSGS_E_ARG;
+    if (!ctx->d_trace) return BSGS_E_STATE;
+    uint32_t n = ctx->NT / 32; *nwarps = n;
+    if (cap_warps < n) return BSGS_E_ARG;
+    CU(cudaSetDevice(ctx->dev));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(out, ctx->d_trace, (size_t)n * 32, cudaMemcpyDeviceToHost));
     return BSGS_OK;
 }

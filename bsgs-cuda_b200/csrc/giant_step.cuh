@@ -90,6 +90,7 @@ struct Tables {
     uint32_t mask;            // H - 1
     uint32_t exact_thr;       // acceptance threshold of fp::fe_key_from_wide: FP_KEY_THR; 0 forces the exact path (tests)
     uint64_t* keys_out;       // emit mode: keys_out[m - 1] = low 64 bits of X(m*G), m <= nkeys
+    uint64_t* trace;          // diagnostics (null in production): 4 words per warp = SM id, globaltimer at start / after pass 1 / at end
     uint64_t nkeys;
 };
 
@@ -291,6 +292,11 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
     const uint32_t t = blockIdx.x * BLOCK + threadIdx.x;
     const uint32_t NT = tb.NT;
     const int PP = (int)tb.PP;
+    if (tb.trace && (threadIdx.x & 31) == 0) {
+        uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        uint64_t now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        tb.trace[4 * (size_t)(t >> 5)] = smid; tb.trace[4 * (size_t)(t >> 5) + 1] = now;
+    }
     for (int i = threadIdx.x; i < W * 32; i += BLOCK) s_win[i] = reinterpret_cast<const uint32_t*>(&wp)[i];
     __syncthreads();
     uint64_t* ring = s_ring + threadIdx.x;
@@ -334,6 +340,7 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
         }
     }
 
+    if (tb.trace && (threadIdx.x & 31) == 0) { uint64_t now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); tb.trace[4 * (size_t)(t >> 5) + 2] = now; }
     // ---------------- one inversion per thread ----------------
     Fe inv; fp::fe_inv(inv.v, acc.v);                                // (a by-value wrapper keeps inv out of local memory but costs 3 spills at 80 registers: measured slower)
 
@@ -453,6 +460,7 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
         }
         if (sw == s_win) { sw = sw_top; kidx -= NT; } else sw -= 32;
     }
+    if (tb.trace && (threadIdx.x & 31) == 0) { uint64_t now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); tb.trace[4 * (size_t)(t >> 5) + 3] = now; }
 }
 
 // probe-only kernels on the fingerprint layout (measurement + parity of the table layout)

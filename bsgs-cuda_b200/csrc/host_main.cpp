@@ -480,11 +480,11 @@ int run(const std::vector<std::string>& argv) {
             std::vector<bsgs_hit> hits(4096);
             uint64_t d0 = 0;
             while (d0 < nwin && !stop) {
-                const uint32_t chunk = (uint32_t)std::min<uint64_t>(nwin - d0, 16);
+                const uint32_t chunk = (uint32_t)std::min<uint64_t>(nwin - d0, 128);      // 8 launches of 16 windows, two in flight inside bsgs_run
                 Pt P = s.window_point(d0);
                 uint8_t p0[64], dd[64]; memcpy(p0, P.x.v, 32); memcpy(p0 + 32, P.y.v, 32); memcpy(dd, s.D.x.v, 32); memcpy(dd + 32, s.D.y.v, 32);
                 uint32_t nh = 0; uint64_t wd = 0;
-                int e = bsgs_run(ctx[r], p0, dd, chunk, chunk, 1, hits.data(), (uint32_t)hits.size(), &nh, &wd);
+                int e = bsgs_run(ctx[r], p0, dd, chunk, std::min<uint32_t>(chunk, 16), 1, hits.data(), (uint32_t)hits.size(), &nh, &wd);
                 if (e != BSGS_OK && e != BSGS_E_OVERFLOW) { fprintf(stderr, "bsgs_run: %s\n", bsgs_strerror(e)); stop = true; return; }
                 if (e == BSGS_E_OVERFLOW && hits.size() < (1u << 22)) { hits.resize(hits.size() * 4); continue; }      // rerun this chunk with a bigger record buffer
                 nh = std::min<uint32_t>(nh, (uint32_t)hits.size());

@@ -37,7 +37,7 @@ class DevInfo(C.Structure):
 EXPORTS = ["bsgs_create", "bsgs_destroy", "bsgs_strerror", "bsgs_last_cuda_error", "bsgs_upload_giants", "bsgs_upload_ht", "bsgs_upload_htcpu",
            "bsgs_giants_staging", "bsgs_giants_commit", "bsgs_ht_staging", "bsgs_ht_commit", "bsgs_step", "bsgs_step_multi",
            "bsgs_giants_generate", "bsgs_giants_export", "bsgs_ht_build_from_keys", "bsgs_ht_generate", "bsgs_ht_build_synthetic", "bsgs_ht_export", "bsgs_ht_device_image",
-           "bsgs_run", "bsgs_time_launches", "bsgs_probe_bench", "bsgs_probe_keys", "bsgs_get_info", "bsgs_set_option", "bsgs_debug_field", "bsgs_debug_key", "bsgs_device_count", "bsgs_device_query", "bsgs_bcast_ht"]
+           "bsgs_run", "bsgs_time_launches", "bsgs_probe_bench", "bsgs_probe_keys", "bsgs_get_info", "bsgs_set_option", "bsgs_debug_field", "bsgs_debug_key", "bsgs_debug_trace", "bsgs_device_count", "bsgs_device_query", "bsgs_bcast_ht"]
 
 _lib = None
 
@@ -82,6 +82,7 @@ def load():
     L.bsgs_debug_field.argtypes = [C.c_int, C.c_int, vp, vp, vp, u32]
     L.bsgs_debug_key.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, u32, C.c_int]
     L.bsgs_bcast_ht.argtypes = [C.POINTER(vp), C.c_int]
+    L.bsgs_debug_trace.argtypes = [vp, vp, u32, C.POINTER(u32)]
     L.bsgs_device_count.argtypes = [C.POINTER(C.c_int)]
     L.bsgs_device_query.argtypes = [C.c_int, C.POINTER(DevInfo)]
     _lib = L
@@ -295,6 +296,13 @@ class Engine:
         out = np.zeros(len(keys), dtype=np.uint8)
         self._ck(self.L.bsgs_probe_keys(self.h, keys.ctypes.data, len(keys), out.ctypes.data), "bsgs_probe_keys")
         return out.astype(bool)
+
+    def trace(self):
+        """(nwarps, 4) array of {SM id, t_start, t_pass1, t_end} (ns) of the last launch (option trace=1)."""
+        n = self.info()["grid"] * self.info()["block"] // 32
+        out = np.zeros((n, 4), dtype=np.uint64); got = C.c_uint32()
+        self._ck(self.L.bsgs_debug_trace(self.h, out.ctypes.data, n, C.byref(got)), "bsgs_debug_trace")
+        return out[:got.value]
 
     def info(self):
         i = Info()

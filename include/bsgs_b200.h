@@ -163,6 +163,10 @@ int  bsgs_debug_field(int device, int op, const uint32_t *a, const uint32_t *b, 
  * asked for the exact path; force != 0 sends every input there.  Parity test of that rare path. */
 int  bsgs_debug_key(int device, int mode, const uint32_t *in, const uint32_t *A, const uint32_t *Q, uint64_t *keys, uint8_t *exact, uint32_t n, int force);
 
+/* per-warp {SM id, %globaltimer (ns) at kernel start, after PASS 1, at the end} of the last giant-step launch, 4 words
+ * per warp; enabled with bsgs_set_option(ctx, "trace", 1).  Used to measure how evenly the warps of an SM progress. */
+int  bsgs_debug_trace(bsgs_ctx *ctx, uint64_t *out, uint32_t cap_warps, uint32_t *nwarps);
+
 #ifdef __cplusplus
 }
 #endif

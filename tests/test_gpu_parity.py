@@ -386,10 +386,24 @@ def test_run_equals_stepwise(pkg, orc):
     g2 = orc.build_g2(T, B, p, w)
     with pkg.Engine(T, B, p, w, htsz) as e:
         e.upload_giants(g2); e.upload_ht(gpu)
-        hits, done = e.run(s.P0, s.D, 7, batch=3)
+        hits, done = e.run(s.P0, s.D, 7, batch=3)                 # two launches in flight (alternating lanes), ragged last batch
         assert done == 7
         exp = sorted((j, c, 0 if c == 5 else i) for j in range(7) for c, i in orc.launch(g2, T, B, p, gpu, htsz, pts[j]))
         assert sorted((win, c, 0 if c == 5 else i) for c, i, win in hits) == exp and len(exp) >= 7
+        e._ck(e.L.bsgs_set_option(e.h, b"overlap", 0), "overlap")  # one launch at a time: same records
+        hits1, done1 = e.run(s.P0, s.D, 7, batch=3)
+        assert done1 == 7 and sorted(hits1) == sorted(hits)
+        e._ck(e.L.bsgs_set_option(e.h, b"overlap", 1), "overlap")
+        for batch in (1, 2, 7):
+            h2, d2 = e.run(s.P0, s.D, 7, batch=batch)
+            assert d2 == 7 and sorted(h2) == sorted(hits)
+        # early stop: the windows of the launch already in flight are searched and counted too
+        first = min(win for c, i, win in hits)
+        h3, d3 = e.run(s.P0, s.D, 7, batch=1, stop_after_hits=1)
+        assert first + 1 <= d3 <= first + 2 and sorted(h3) == sorted(x for x in hits if x[2] < d3)
+        e.set_verify(False)
+        ms = e.time_launches(pts[:6], 2, 3)                        # timing entry point alternates lanes as well
+        assert ms > 0 and sorted((c, i) for c, i in e.step(pts[0])) == sorted((c, i) for c, i, win in hits if win == 0)
 
 
 def test_error_behaviour(pkg):
