@@ -235,7 +235,7 @@ static int alloc_giants(bsgs_ctx* ctx) {
     if (!ctx->d_gx) {
         CU(cudaMalloc(&ctx->d_gx, slots * 32));
         CU(cudaMalloc(&ctx->d_gy, slots * 32));
-        ctx->chain_bytes = slots * 32 * ctx->max_windows;
+        ctx->chain_bytes = slots * 32 * ctx->max_windows + 2 * (size_t)ctx->NT * 32;      // two leading rows: pad + the element "1" (giant_step.cuh)
         CU(cudaMalloc(&ctx->d_chain, ctx->chain_bytes));
         ctx->giants_bytes = slots * 64;
     }
@@ -421,7 +421,7 @@ static int generate_baby_keys(bsgs_ctx* ctx, uint64_t* d_keys) {
     auto cleanup = [&]() { cudaFree(gx); cudaFree(gy); cudaFree(chain); };
     cudaError_t e = cudaMalloc(&gx, slots * 32);
     if (e == cudaSuccess) e = cudaMalloc(&gy, slots * 32);
-    if (e == cudaSuccess) e = cudaMalloc(&chain, slots * 32 * W);
+    if (e == cudaSuccess) e = cudaMalloc(&chain, slots * 32 * W + 2 * (size_t)ctx->NT * 32);
     if (e != cudaSuccess) { cleanup(); ctx->last_cuda = (int)e; cudaGetLastError(); return BSGS_E_NOMEM; }
     int rc = generate_multiples(ctx, gx, gy, hec::kG);
     if (rc) { cleanup(); return rc; }
@@ -534,11 +534,7 @@ static cudaError_t launch_k(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy, int 
 }
 static cudaError_t launch_any(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy, int lane = 0) {
     if (nwin < 1 || nwin > BSGS_MAX_WINDOWS) return cudaErrorInvalidValue;
-#if !GS_STAGE                                                                           // (the staging slots of 320 threads exceed the static shared-memory limit)
     if (c->block == 320) return launch_k<320, 2>(c, nwin, pxy, lane);                  // 5 warps per scheduler, 96 registers
-#else
-    if (c->block == 320) return cudaErrorInvalidValue;
-#endif
     switch (c->blocks_per_sm) {
         case 1: case 2: return launch_k<256, 2>(c, nwin, pxy, lane);
         case 3: return launch_k<256, 3>(c, nwin, pxy, lane);

@@ -45,12 +45,9 @@
 #define GS_ABLATE 0
 #endif
 
-// GS_STAGE = 1: the fingerprint sector of every key is copied asynchronously (cp.async, 2 x 16 bytes, L2 only)
-// into a per-thread slot of shared memory at the moment the key is known; the drain reads shared memory
-// instead of issuing the 256-bit global load itself.  Needs GS_RING <= 4 at three 256-thread CTAs per SM
-// (32 bytes x ring x threads of shared memory).  0: the drain loads the sectors (bursts of GS_GROUP).
-#ifndef GS_STAGE
-#define GS_STAGE 0
+// GS_PREFETCH: L2 prefetch of the chain element one iteration ahead (PASS 2 walks the chain backwards)
+#ifndef GS_PREFETCH
+#define GS_PREFETCH 1
 #endif
 
 namespace gs {
@@ -183,13 +180,6 @@ __global__ void k_build_fp_sectors(const uint32_t* __restrict__ off, const uint3
 
 struct FpSector {
     uint4 a, b;
-    // asynchronous copy of bucket h's sector into this thread's staging slot (two uint4 words BLOCK apart)
-    static __device__ __forceinline__ void stage(const Tables& tb, uint32_t h, uint4* slot, int stride) {
-        const uint4* p = reinterpret_cast<const uint4*>(tb.buckets) + 2ull * h;
-        const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(slot), d1 = (uint32_t)__cvta_generic_to_shared(slot + stride);
-        asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d0), "l"(p) : "memory");
-        asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d1), "l"(p + 1) : "memory");
-    }
     __device__ __forceinline__ void load(const Tables& tb, uint32_t h) {
         const uint4* p = reinterpret_cast<const uint4*>(tb.buckets) + 2ull * h;
         // One random 32-byte sector, never reused: a single 256-bit load (LDG.E.256) kept out of L1,
@@ -285,10 +275,6 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParams wp, int W) {
     __shared__ __align__(16) uint32_t s_win[kMaxW * 32];
     __shared__ uint64_t s_ring[MODE == 0 ? kRing * BLOCK : 1];
-#if GS_STAGE
-    __shared__ uint4 s_sec[MODE == 0 ? kRing * 2 * BLOCK : 1];     // [slot][half][thread]
-    uint4* const sec_slot = s_sec + threadIdx.x;
-#endif
     const uint32_t t = blockIdx.x * BLOCK + threadIdx.x;
     const uint32_t NT = tb.NT;
     const int PP = (int)tb.PP;
@@ -324,7 +310,9 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
     for (int i = 1; i < 8; i++) acc.v[i] = 0;
     {
         const uint4* gxp = tb.gx + t;
-        uint4* cp = tb.chain + t;
+        uint4* cp = tb.chain + NT2 + t;
+        if (!(GS_ABLATE & 2)) st8_stream(cp, cp + NT, acc.v);        // chain element -1 = 1: PASS 2 needs no special case for its last step
+        cp += NT2;
 #pragma unroll 1
         for (int r = 0; r < PP; r++, gxp += NT2) {
             const Fe qx = ldg_fe((GS_ABLATE & 4) ? tb.gx + t : gxp, (GS_ABLATE & 4) ? tb.gx + t + NT : gxp + NT);
@@ -345,120 +333,106 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
     Fe inv; fp::fe_inv(inv.v, acc.v);                                // (a by-value wrapper keeps inv out of local memory but costs 3 spills at 80 registers: measured slower)
 
     // ---------------- PASS 2: unwind, slopes, X, keys -> ring -> probe bursts ----------------
-    // Loop-carried state is kept small (80 registers, 3 CTAs per SM): the giant index of the row, one
-    // pointer into the chain, the window-constant pointer (which doubles as the window counter) and
-    // the ring fill.  The rare cases -- a padding row (giant index >= N), a
-    // tangent (Px == Qx) or the ragged last burst -- only raise `special`; the drain then classifies
-    // every slot from its chain index (drain_slow) instead of the loop tracking per-slot masks.
+    // Rows outside, windows inside; loop-carried state is kept small (80 registers, 3 CTAs per SM): the giant
+    // index of the row, one pointer into the chain, the chain index and the ring fill.  The rare cases -- a
+    // padding row (giant index >= N), a tangent (Px == Qx) or the ragged last burst -- only raise `special`;
+    // the drain then classifies every slot from its chain index (drain_slow) instead of the loop tracking
+    // per-slot masks.  The chain carries two extra leading rows: element -1 = 1 (so that the last step loads
+    // its "previous product" like every other) and one pad row (so that the L2 prefetch needs no guard).
     int fill = 0;
     bool special = false;
+    int ci = PP * W - 1;
     uint32_t kidx = (uint32_t)(PP - 1) * NT + t;                    // giant index of the current row
-    const uint4* cp = tb.chain + (size_t)(PP * W - 1) * NT2 + t;  // &chain[ci]; chain[ci-1] is one stride below
+    const uint4* cp = tb.chain + (size_t)(PP * W + 1) * NT2 + t;  // &element[ci]; element[ci-1] is one stride below
     const uint32_t* const sw_top = s_win + (W - 1) * 32;
-    const uint32_t* sw = sw_top;
-    Fe qx, qy;                                                     // the row's giant point, held across its windows
+
+    // drain: slot 2j / 2j+1 = minus / plus key of chain index ci_first - j
+    auto drain = [&](int ci_first) {
 #pragma unroll 1
-    for (int ci = PP * W - 1; ci >= 0; ci--) {
-        Fe cprev;                                                  // chain[ci-1], or 1 for the very first element
-        cp -= NT2;
-        if (ci > 0 && !(GS_ABLATE & 2)) {
-            ld8_stream(cprev.v, cp, cp + NT);
-            if (ci > 1) { prefetch_l2(cp - NT2); prefetch_l2(cp - NT); }
-        } else if (GS_ABLATE & 2) {
-            cprev = inv;
-        } else {
-            cprev.v[0] = 1;
+        for (int s0 = 0; s0 < fill; s0 += kGroup) {
+            FpSector sec[kGroup]; uint64_t key[kGroup];
 #pragma unroll
-            for (int i = 1; i < 8; i++) cprev.v[i] = 0;
-        }
-        if (sw == sw_top) {                                         // new row: slot (r, t) lives at (2r)*NT + t = 2*kidx - t
-            const size_t go = (GS_ABLATE & 4) ? (size_t)t : 2 * (size_t)kidx - t;
-            qx = ldg_fe(tb.gx + go, tb.gx + go + NT); qy = ldg_fe(tb.gy + go, tb.gy + go + NT);
-            if (MODE == 0 && kidx >= tb.N) special = true;
-        }
-        Fe d;
-        { Fe px = lds_fe(sw); fp::fe_sub_canon(d.v, px.v, qx.v); }
-        const bool eq = fp::fe_is_zero_rare(d.v);
-        if (eq) d = lds_fe(sw + 24);
-        Fe invd;
-        fp::fe_mul(invd.v, inv.v, cprev.v);                        // 1 / d_ci
-        { Fe x; fp::fe_mul(x.v, inv.v, d.v); inv = x; }            // 1 / (d_0 ... d_{ci-1})
-        uint64_t* rp = ring + fill * BLOCK;
-        if (!eq) {
-            // X = lambda^2 + (p - Px) - Qx is never formed, lambda^2 not even reduced: the low 64 bits of X follow
-            // from a few limbs of the 512-bit square and of the other two terms (fp::fe_key_from_wide); the part
-            // common to both candidates:
-            const uint64_t t_lo = *reinterpret_cast<const uint64_t*>(sw + 16) - (((uint64_t)qx.v[1] << 32) | qx.v[0]);
-            const int64_t t7 = (int64_t)sw[23] - (int64_t)qx.v[7];
-#pragma unroll
-            for (int side = 0; side < 2; side++) {                  // side 0: P - Q (code 2), slope (Py + Qy)/d ; side 1: P + Q (code 1), slope (Py - Qy)/d
-                Fe py = lds_fe(sw + 8), sum, lam;
-                if (side == 0) fp::fe_add_lazy(sum.v, py.v, qy.v);
-                else fp::fe_sub_canon(sum.v, py.v, qy.v);
-                fp::fe_mul(lam.v, sum.v, invd.v);
-                const uint64_t key = candidate_key(lam, t_lo, t7, sw + 16, qx, tb.exact_thr);
-                if (MODE == 0) {
-                    rp[side * BLOCK] = key;
-#if GS_STAGE
-                    FpSector::stage(tb, (uint32_t)key & tb.mask, sec_slot + (fill + side) * 2 * BLOCK, BLOCK);
-#endif
-                } else if (kidx < tb.N) {                             // multiplier C - (i+1) (side 0) or C + (i+1) (side 1)
-                    const uint64_t i1 = (uint64_t)kidx + 1, c = wp.center[(sw - s_win) >> 5];
-                    const uint64_t m = side == 0 ? c - i1 : c + i1;
-                    if (m <= tb.nkeys) tb.keys_out[m - 1] = key;
-                }
+            for (int j = 0; j < kGroup; j++) {
+                key[j] = ring[(s0 + j) * BLOCK];
+                sec[j].load(tb, (uint32_t)key[j] & tb.mask);
             }
-        } else {
-            Fe px = lds_fe(sw);
-            const uint64_t key = double_x_low64_v(px, invd);        // X(2P)  (code 4); cannot occur in emit mode
+            uint32_t need = special ? (1u << kGroup) - 1u : 0u;
+#pragma unroll
+            for (int j = 0; j < kGroup; j++) need |= (sec[j].maybe((uint32_t)(key[j] >> 32)) ? 1u : 0u) << j;
+            // One warp-wide vote per group; the rare branch ends in an explicit __syncwarp(): without
+            // it lanes that took the out-of-line path were observed (ncu: 31.93 active lanes in the
+            // arithmetic, one SM busy 3x longer than the rest) to stay split from their warp for the
+            // remainder of the loop.
+            if (__any_sync(0xFFFFFFFFu, need != 0u)) {
+#pragma unroll 1
+                for (int j = 0; j < kGroup; j++)
+                    if ((need >> j) & 1u) drain_slow(tb, s_win, W, t, ci_first, s0 + j, fill, key[j]);
+                __syncwarp();
+            }
+        }
+        fill = 0; special = false;
+    };
+
+#pragma unroll 1
+    for (int r = PP - 1; r >= 0; r--, kidx -= NT) {
+        // the row's giant point, held across its windows: slot (r, t) lives at (2r)*NT + t = 2*kidx - t
+        const size_t go = (GS_ABLATE & 4) ? (size_t)t : 2 * (size_t)kidx - t;
+        const Fe qx = ldg_fe(tb.gx + go, tb.gx + go + NT), qy = ldg_fe(tb.gy + go, tb.gy + go + NT);
+        if (MODE == 0 && kidx >= tb.N) special = true;
+#pragma unroll 1
+        for (const uint32_t* sw = sw_top; sw >= s_win; sw -= 32, ci--) {
+            Fe cprev;                                              // element[ci-1]
+            cp -= NT2;
+            if (!(GS_ABLATE & 2)) {
+                ld8_stream(cprev.v, cp, cp + NT);
+                if (GS_PREFETCH) { prefetch_l2(cp - NT2); prefetch_l2(cp - NT); }
+            } else cprev = inv;
+            Fe d;
+            { Fe px = lds_fe(sw); fp::fe_sub_canon(d.v, px.v, qx.v); }
+            const bool eq = fp::fe_is_zero_rare(d.v);
+            if (eq) d = lds_fe(sw + 24);
+            Fe invd;
+            fp::fe_mul(invd.v, inv.v, cprev.v);                    // 1 / d_ci
+            { Fe x; fp::fe_mul(x.v, inv.v, d.v); inv = x; }        // 1 / (d_0 ... d_{ci-1})
+            uint64_t* rp = ring + fill * BLOCK;
+            if (!eq) {
+                // X = lambda^2 + (p - Px) - Qx is never formed, lambda^2 not even reduced: the low 64 bits of X follow
+                // from a few limbs of the 512-bit square and of the other two terms (fp::fe_key_from_wide); the part
+                // common to both candidates:
+                const uint64_t t_lo = *reinterpret_cast<const uint64_t*>(sw + 16) - (((uint64_t)qx.v[1] << 32) | qx.v[0]);
+                const int64_t t7 = (int64_t)sw[23] - (int64_t)qx.v[7];
+#pragma unroll
+                for (int side = 0; side < 2; side++) {              // side 0: P - Q (code 2), slope (Py + Qy)/d ; side 1: P + Q (code 1), slope (Py - Qy)/d
+                    Fe py = lds_fe(sw + 8), sum, lam;
+                    if (side == 0) fp::fe_add_lazy(sum.v, py.v, qy.v);
+                    else fp::fe_sub_canon(sum.v, py.v, qy.v);
+                    fp::fe_mul(lam.v, sum.v, invd.v);
+                    const uint64_t key = candidate_key(lam, t_lo, t7, sw + 16, qx, tb.exact_thr);
+                    if (MODE == 0) rp[side * BLOCK] = key;
+                    else if (kidx < tb.N) {                         // multiplier C - (i+1) (side 0) or C + (i+1) (side 1)
+                        const uint64_t i1 = (uint64_t)kidx + 1, c = wp.center[(sw - s_win) >> 5];
+                        const uint64_t m = side == 0 ? c - i1 : c + i1;
+                        if (m <= tb.nkeys) tb.keys_out[m - 1] = key;
+                    }
+                }
+            } else {
+                Fe px = lds_fe(sw);
+                const uint64_t key = double_x_low64_v(px, invd);    // X(2P)  (code 4); cannot occur in emit mode
+                if (MODE == 0) rp[0] = key;
+                special = true;
+            }
             if (MODE == 0) {
-                rp[0] = key;
-#if GS_STAGE
-                FpSector::stage(tb, (uint32_t)key & tb.mask, sec_slot + fill * 2 * BLOCK, BLOCK);
-#endif
-            }
-            special = true;
-        }
-        if (MODE == 0) {
-            fill += 2;
-            if ((fill == kRing || ci == 0) && (GS_ABLATE & 1)) { fill = 0; special = false; }
-            if (fill == kRing || ci == 0) {
-                // drain: slot 2j / 2j+1 = minus / plus key of chain index ci_first - j
-                const int ci_first = ci + (fill >> 1) - 1;
-                if (ci == 0) special = true;                        // the last burst may end inside a group of four
-#if GS_STAGE
-                asm volatile("cp.async.wait_all;" ::: "memory");     // this thread's own copies; nobody else reads its slots
-#endif
-#pragma unroll 1
-                for (int s0 = 0; s0 < fill; s0 += kGroup) {
-                    FpSector sec[kGroup]; uint64_t key[kGroup];
-#pragma unroll
-                    for (int j = 0; j < kGroup; j++) {
-                        key[j] = ring[(s0 + j) * BLOCK];
-#if GS_STAGE
-                        sec[j].a = sec_slot[(s0 + j) * 2 * BLOCK]; sec[j].b = sec_slot[((s0 + j) * 2 + 1) * BLOCK];
-#else
-                        sec[j].load(tb, (uint32_t)key[j] & tb.mask);
-#endif
-                    }
-                    uint32_t need = special ? (1u << kGroup) - 1u : 0u;
-#pragma unroll
-                    for (int j = 0; j < kGroup; j++) need |= (sec[j].maybe((uint32_t)(key[j] >> 32)) ? 1u : 0u) << j;
-                    // One warp-wide vote per group; the rare branch ends in an explicit __syncwarp(): without
-                    // it lanes that took the out-of-line path were observed (ncu: 31.93 active lanes in the
-                    // arithmetic, one SM busy 3x longer than the rest) to stay split from their warp for the
-                    // remainder of the loop.
-                    if (__any_sync(0xFFFFFFFFu, need != 0u)) {
-#pragma unroll 1
-                        for (int j = 0; j < kGroup; j++)
-                            if ((need >> j) & 1u) drain_slow(tb, s_win, W, t, ci_first, s0 + j, fill, key[j]);
-                        __syncwarp();
-                    }
+                fill += 2;
+                if (fill == kRing) {
+                    if (GS_ABLATE & 1) { fill = 0; special = false; }
+                    else drain(ci + (kRing >> 1) - 1);
                 }
-                fill = 0; special = false;
             }
         }
-        if (sw == s_win) { sw = sw_top; kidx -= NT; } else sw -= 32;
+    }
+    if (MODE == 0 && fill && !(GS_ABLATE & 1)) {                    // the ragged last burst may end inside a group of four: every slot classified exactly
+        special = true;
+        drain((fill >> 1) - 1);
     }
     if (tb.trace && (threadIdx.x & 31) == 0) { uint64_t now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); tb.trace[4 * (size_t)(t >> 5) + 3] = now; }
 }
