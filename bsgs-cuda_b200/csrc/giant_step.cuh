@@ -366,7 +366,7 @@ k_giant_step(const __grid_constant__ Tables tb, const __grid_constant__ WinParam
             if (__any_sync(0xFFFFFFFFu, need != 0u)) {
 #pragma unroll 1
                 for (int j = 0; j < kGroup; j++)
-                    if ((need >> j) & 1u) drain_slow(tb, s_win, W, t, ci_first, s0 + j, fill, key[j]);
+                    if ((need >> j) & 1u) drain_slow(tb, s_win, W, t, ci_first, s0 + j, fill, ring[(s0 + j) * BLOCK]);    // (key re-read: no indexed register array)
                 __syncwarp();
             }
         }
