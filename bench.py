@@ -12,7 +12,9 @@ contiguous sub-range of windows with the same per-GPU tables (weak scaling, no p
 one NCCL broadcast of the htGPU image at start-up).
 
 Timing: device time with CUDA events on the launching stream (inside libbsgs_b200.so), bracketed by
-barrier + synchronize, max over ranks.  Inputs (5.4 GB table + 1.2 GB giants) are far larger than
+barrier + synchronize, max over ranks.  The library keeps two launches in flight on two streams (the warps
+of a launch finish unevenly; the CTAs of the next launch take the freed slots), so K steps are timed as a
+whole: first event before launch 1 on either stream, last event after launch K on both.  Inputs (5.4 GB table + 1.2 GB giants) are far larger than
 the 126 MB L2.  `e2e` goes through the reference-facing C-ABI call bsgs_run() with HOST buffers:
 base point and stride in host memory in, hit records in host memory out, every launch's parameter
 upload and record read-back inside the timed region.
@@ -222,6 +224,7 @@ def run_b200(args):
             "config": {"workload": wl["name"], "T": T, "B": B, "p": p, "w": w, "htsz": htsz, "windows_per_launch": nwin,
                        "giant_steps_per_launch": steps_per_launch, "keys_per_giant_step": 2 * w, "l2": "inputs (6.6 GB) larger than L2",
                        "grid": info["grid"], "block": info["block"], "points_per_thread": info["points_per_thread"],
+                       "launches_in_flight": 2,
                        "parallelism": f"{world} x disjoint window ranges"},
             "keys_per_s": value * 2 * w,
             "e2e": {"value": e2e, "unit": "giant-steps/s", "h2d_bytes_per_step": 128 * nwin, "d2h_bytes_per_step": 16 + 64 * 12,

@@ -70,6 +70,9 @@ FP_DEV void subc_cc(uint32_t& r, uint32_t a, uint32_t b) { uint64_t t = (uint64_
 FP_DEV void subc(uint32_t& r, uint32_t a, uint32_t b) { r = a - b - g_cc; }
 #endif
 
+#ifndef FP_SQR_LINK
+#define FP_SQR_LINK 1
+#endif
 #ifndef FP_LINK
 #define FP_LINK 0
 #endif
@@ -202,11 +205,12 @@ FP_DEV void fe_mul(uint32_t r[8], const uint32_t a[8], const uint32_t b[8]) {
     for (int i = 0; i < 8; i += 2) {
         // FP_LINK 0: rows independent; 1: every row takes the zero carry left by its predecessor (one dependency
         // chain, one live carry predicate; ptxas otherwise interleaves many rows and spills predicates)
+        // (FP_LINK 2: only the pairs on the same accumulator are linked: R2 -> R3 and R4 -> R1 of the next round)
         if (i == 0) mad_row<false, false>(e + i, a, b[i], cw[0]);
         else mad_row<true, FP_LINK != 0>(e + i, a, b[i], cw[i]);
-        mad_row<false, FP_LINK != 0>(o + i, a + 1, b[i], cw[0]);
+        mad_row<false, FP_LINK == 1>(o + i, a + 1, b[i], cw[0]);
         mad_row<true, FP_LINK != 0>(o + i, a, b[i + 1], cw[i + 1]);
-        mad_row<false, FP_LINK != 0>(e + i + 2, a + 1, b[i + 1], cw[0]);
+        mad_row<false, FP_LINK == 1>(e + i + 2, a + 1, b[i + 1], cw[0]);
     }
     // v = e + (o << 32) + (cw << 256)
     uint32_t v[16];
@@ -244,13 +248,15 @@ FP_DEV void fe_sqr_wide(uint32_t v[16], const uint32_t a[8]) {      // v = a^2, 
     // the previous one.  That changes no value, but it makes the cross products of one parity a single
     // dependency chain with one live carry; left independent, ptxas interleaves all seven chains and spills
     // carry predicates into a register (two LOP3 per spill).
+#define SQ_F (FP_SQR_LINK == 0)     /* first product of a chain after the first: fresh flag (1) or linked (0) */
     SQ_E(2, 4, 1); SQ_E(3, 5, 0); SQ_END                                                                  // [6..8]
-    SQ_E(1, 3, 0); SQ_E(1, 5, 0); SQ_E(2, 6, 0); SQ_E(4, 6, 0); SQ_END                                    // [4..10]
-    SQ_E(0, 2, 0); SQ_E(0, 4, 0); SQ_E(0, 6, 0); SQ_E(1, 7, 0); SQ_E(3, 7, 0); SQ_E(5, 7, 0); SQ_END      // [2..12]
+    SQ_E(1, 3, SQ_F); SQ_E(1, 5, 0); SQ_E(2, 6, 0); SQ_E(4, 6, 0); SQ_END                                 // [4..10]
+    SQ_E(0, 2, SQ_F); SQ_E(0, 4, 0); SQ_E(0, 6, 0); SQ_E(1, 7, 0); SQ_E(3, 7, 0); SQ_E(5, 7, 0); SQ_END   // [2..12]
     SQ_O(3, 4, 1); SQ_END                                                                                 // [6]
-    SQ_O(2, 3, 0); SQ_O(2, 5, 0); SQ_O(4, 5, 0); SQ_END                                                   // [4..8]
-    SQ_O(1, 2, 0); SQ_O(1, 4, 0); SQ_O(1, 6, 0); SQ_O(3, 6, 0); SQ_O(5, 6, 0); SQ_END                     // [2..10]
-    SQ_O(0, 1, 0); SQ_O(0, 3, 0); SQ_O(0, 5, 0); SQ_O(0, 7, 0); SQ_O(2, 7, 0); SQ_O(4, 7, 0); SQ_O(6, 7, 0); SQ_END   // [0..12]
+    SQ_O(2, 3, SQ_F); SQ_O(2, 5, 0); SQ_O(4, 5, 0); SQ_END                                                // [4..8]
+    SQ_O(1, 2, SQ_F); SQ_O(1, 4, 0); SQ_O(1, 6, 0); SQ_O(3, 6, 0); SQ_O(5, 6, 0); SQ_END                  // [2..10]
+    SQ_O(0, 1, SQ_F); SQ_O(0, 3, 0); SQ_O(0, 5, 0); SQ_O(0, 7, 0); SQ_O(2, 7, 0); SQ_O(4, 7, 0); SQ_O(6, 7, 0); SQ_END   // [0..12]
+#undef SQ_F
 #undef SQ_END
 #undef SQ_O
 #undef SQ_E
