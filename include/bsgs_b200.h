@@ -119,15 +119,21 @@ int  bsgs_step_multi(bsgs_ctx *ctx, uint32_t nwin, const uint8_t *pxy_le,
                      bsgs_hit *out, uint32_t cap, uint32_t *nhits);
 /* Whole search loop on the library side: windows j = 0..nwindows-1 with base points
  * P_j = P0 + j*D (D = PUBADDBIG, F197:4759-4765), `batch` windows per launch, stops early after the
- * launch in which `stop_after_hits` records have been collected (0 = never).  hit.window = j. */
+ * launch in which `stop_after_hits` records have been collected (0 = never).  hit.window = j (the low
+ * 32 bits: callers pass at most 2^32 windows per call).  When nwindows > batch, TWO launches are kept in
+ * flight on two streams with their own chain and record buffers (the warps of a launch finish unevenly;
+ * the CTAs of the next launch take the freed slots): on an early stop the windows of the launch that was
+ * already running are searched, reported and counted in *windows_done as well.  Option "overlap" = 0
+ * restores one launch at a time.  The second chain buffer (as large as the first) is allocated on first use. */
 int  bsgs_run(bsgs_ctx *ctx, const uint8_t p0xy_le[64], const uint8_t dxy_le[64], uint64_t nwindows,
               uint32_t batch, uint32_t stop_after_hits, bsgs_hit *out, uint32_t cap, uint32_t *nhits,
               uint64_t *windows_done);
 
 /* -- measurement helpers (used by bench.py; device-resident timing with CUDA events) -------- */
-/* `iters` back-to-back launches of nwin windows each on the context's stream (pxy_le holds
- * iters*nwin base points, 64 bytes each); returns the elapsed device time of the whole train in *ms
- * (CUDA events on the launching stream).  Hit records are discarded. */
+/* `iters` launches of nwin windows each (pxy_le holds iters*nwin base points, 64 bytes each), alternating
+ * between the context's two streams like bsgs_run; returns the elapsed device time of the whole train in *ms
+ * (CUDA events: the first before anything starts on either stream, the last after both streams are done).
+ * Hit records are discarded. */
 int  bsgs_time_launches(bsgs_ctx *ctx, uint32_t nwin, const uint8_t *pxy_le, uint32_t iters, float *ms);
 /* probe-only micro-kernel: nkeys pseudo-random 64-bit keys (splitmix64 of seed)
  * probed against the uploaded table; returns device ms and the number of keys that probed true. */
@@ -144,7 +150,9 @@ int  bsgs_get_info(const bsgs_ctx *ctx, bsgs_info *info);
 typedef struct { char name[128]; int32_t cc_major, cc_minor, sm_count, reserved; uint64_t free_bytes, total_bytes; } bsgs_devinfo;
 int  bsgs_device_count(int *count);
 int  bsgs_device_query(int device, bsgs_devinfo *out);
-/* "verify" (0|1, any time; needs payloads: a device-side build or bsgs_upload_htcpu).
+/* any time: "verify" (0|1; needs payloads: a device-side build or bsgs_upload_htcpu), "overlap" (1|0: two launches
+ * in flight in bsgs_run / bsgs_time_launches, default 1), "force_exact" (0|1, tests: every candidate key through
+ * the kernel's out-of-line exact path), "trace" (0|1, diagnostics: per-warp timestamps, bsgs_debug_trace).
  * tuning knobs, call before uploads: "blocks_per_sm" (1..3 resident 256-thread CTAs per SM; the
  * grid is SMs x this), "block" (256, or 320 = two 320-thread CTAs per SM), "max_windows" (sizes the chain buffer), "l2_fetch" (32|64|128: device-wide
  * DRAM->L2 fetch granularity) */
