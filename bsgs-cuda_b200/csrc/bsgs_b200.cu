@@ -542,20 +542,33 @@ static cudaError_t launch_any(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy, in
     }
 }
 
-// second lane, allocated on first use (bsgs_run / bsgs_time_launches with more than one launch)
+// second lane, allocated on first use (bsgs_run / bsgs_time_launches with more than one launch).  When the
+// device has no room for a second chain (very large N) the context quietly stays with one launch at a time.
 static int ensure_lane2(bsgs_ctx* ctx) {
     if (ctx->stream2) return BSGS_OK;
     CU(cudaSetDevice(ctx->dev));
-    CU(cudaMalloc(&ctx->d_chain2, ctx->chain_bytes));
-    CU(cudaMalloc(&ctx->d_hits2, 16 + (size_t)ctx->hit_cap * 12));
-    CU(cudaMalloc(&ctx->d_verdict2, (size_t)ctx->hit_cap * 4));
-    CU(cudaMallocHost(&ctx->h_verdict2, (size_t)ctx->hit_cap * 4));
-    CU(cudaMallocHost(&ctx->h_hits2, 16 + (size_t)ctx->hit_cap * 12));
-    CU(cudaEventCreate(&ctx->e2));
-    cudaStream_t st;
-    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    CU(cudaMemsetAsync(ctx->d_hits2, 0, 16, st));
-    CU(cudaStreamSynchronize(st));
+    cudaStream_t st = nullptr;
+    cudaError_t e = cudaMalloc(&ctx->d_chain2, ctx->chain_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_hits2, 16 + (size_t)ctx->hit_cap * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_verdict2, (size_t)ctx->hit_cap * 4);
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_verdict2, (size_t)ctx->hit_cap * 4);
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_hits2, 16 + (size_t)ctx->hit_cap * 12);
+    if (e == cudaSuccess && !ctx->e2) e = cudaEventCreate(&ctx->e2);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_hits2, 0, 16, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(ctx->d_chain2); cudaFree(ctx->d_hits2); cudaFree(ctx->d_verdict2);
+        if (ctx->h_verdict2) cudaFreeHost(ctx->h_verdict2);
+        if (ctx->h_hits2) cudaFreeHost(ctx->h_hits2);
+        if (st) cudaStreamDestroy(st);
+        ctx->d_chain2 = nullptr; ctx->d_hits2 = ctx->d_verdict2 = ctx->h_verdict2 = ctx->h_hits2 = nullptr;
+        cudaGetLastError();
+        if (e == cudaErrorMemoryAllocation) { ctx->overlap = false; return BSGS_OK; }     // no room: one lane
+        ctx->last_cuda = (int)e;
+        return BSGS_E_CUDA;
+    }
     ctx->stream2 = st;
     return BSGS_OK;
 }
@@ -627,8 +640,8 @@ extern "C" int bsgs_run(bsgs_ctx* ctx, const uint8_t p0xy_le[64], const uint8_t 
     auto fill = [&](uint8_t* buf, uint32_t n) {                 // GetJob (F197:2077-2092), n windows ahead
         for (uint32_t i = 0; i < n; i++) { hec::store_le(buf + 64 * i, P.x); hec::store_le(buf + 64 * i + 32, P.y); hec::pt_add(P, P, D); }
     };
-    const bool two = ctx->overlap && nwindows > batch;             // two launches in flight, alternating lanes
-    if (two) { int r = ensure_lane2(ctx); if (r) return r; }
+    bool two = ctx->overlap && nwindows > batch;                   // two launches in flight, alternating lanes
+    if (two) { int r = ensure_lane2(ctx); if (r) return r; two = ctx->overlap; }
     uint32_t n = (uint32_t)(nwindows < batch ? nwindows : batch);
     uint64_t issued = 0; int lane = 0;
     if (n) { fill(cur, n); CU(launch_any(ctx, n, cur, 0)); issued = n; }
@@ -667,8 +680,8 @@ extern "C" int bsgs_time_launches(bsgs_ctx* ctx, uint32_t nwin, const uint8_t* p
     if (!ctx || !pxy_le || !ms || nwin < 1 || nwin > ctx->max_windows || !iters) return BSGS_E_ARG;
     if (!ctx->giants_ready || !ctx->ht_ready) return BSGS_E_STATE;
     CU(cudaSetDevice(ctx->dev));
-    const bool two = ctx->overlap && iters > 1;
-    if (two) { int r = ensure_lane2(ctx); if (r) return r; }
+    bool two = ctx->overlap && iters > 1;
+    if (two) { int r = ensure_lane2(ctx); if (r) return r; two = ctx->overlap; }
     CU(cudaEventRecord(ctx->e0, ctx->stream));
     if (two) CU(cudaStreamWaitEvent(ctx->stream2, ctx->e0, 0));      // nothing of the timed region starts before e0
     for (uint32_t i = 0; i < iters; i++) CU(launch_any(ctx, nwin, pxy_le + (size_t)i * nwin * 64, two ? (int)(i & 1) : 0));

@@ -252,10 +252,10 @@ bool tune_b200(unsigned long long free_bytes, int sm, double& wexp, long long& p
         unsigned long long H = 1ull << hs, tb = 4 * (H + 1) + 4 * w + 32 * H + 4 * w;
         if ((double)tb > 0.5 * (double)free_bytes) continue;
         unsigned long long room = (unsigned long long)((double)(free_bytes - tb) * 0.9);
-        unsigned long long nmax = std::min<unsigned long long>(room / (64 + 32 * windows), (1ull << 28) - 1);
+        unsigned long long nmax = std::min<unsigned long long>(room / (64 + 2 * 32 * windows), (1ull << 28) - 1);      // two chains: two launches in flight
         long long pp = (long long)(nmax / (unsigned long long)(t * sm)) & ~1ll;
         if (pp < 2) continue;
-        wexp = we; p = pp; htsz = hs; mb = (double)(tb + (unsigned long long)(t * sm * pp) * (64 + 32 * windows)) / 1048576.0;
+        wexp = we; p = pp; htsz = hs; mb = (double)(tb + (unsigned long long)(t * sm * pp) * (64 + 2 * 32 * windows)) / 1048576.0;
         return true;
     }
     return false;

@@ -9,7 +9,7 @@ Two functions:
   procedure has an input on Hopper/Blackwell at all.
 * `tune_b200(free_bytes, sm)` is the suggestion this build prints: the reference procedure knows
   neither the kernel's structural limits (8*N < 2^31 in the reference PTX, N < 2^31 here, w < 2^32,
-  htsz <= 31) nor this library's memory model (giants 64 B + 32 B of chain per window per giant;
+  htsz <= 31) nor this library's memory model (giants 64 B + 2 x 32 B of chain per window per giant (two launches in flight);
   table = htGPU image + one 32-byte fingerprint sector per bucket + 4 B payload per entry when the
   table is generated on the device), and on a 180 GB part it proposes an N the reference kernel
   cannot index.
@@ -111,12 +111,12 @@ def tune_b200(free_bytes: int, sm: int, windows: int = 16, t: int = 512):
         if tb > 0.5 * free_bytes:
             continue
         room = int((free_bytes - tb) * 0.9)
-        n_max = min(room // (64 + 32 * windows), (1 << 28) - 1)                 # 8*N < 2^31: stay loadable by the reference's own files
+        n_max = min(room // (64 + 2 * 32 * windows), (1 << 28) - 1)                 # 8*N < 2^31: stay loadable by the reference's own files
         p = (n_max // (t * sm)) & ~1
         if p < 2:
             continue
         best = {"t": t, "b": sm, "p": p, "w": wexp, "w_items": w, "htsz": htsz, "windows_per_launch": windows,
-                "device_mb": (tb + t * sm * p * (64 + 32 * windows)) / MB}
+                "device_mb": (tb + t * sm * p * (64 + 2 * 32 * windows)) / MB}
         break
     return best
 

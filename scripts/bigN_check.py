@@ -26,7 +26,18 @@ with b.Engine(T, B, p, w, htsz, device=0) as e:
     t2 = time.time()
     single = sorted((c, i, wi) for wi, pt in enumerate(pts) for c, i in norm_hits(e.step(pt)))
     ok_plant = all((c, k, wi) in multi for wi, c, k in plant)
+    # bsgs_run over two launches: the second chain (another 132 GB) cannot be allocated on a 180 GB part, so the
+    # library must fall back to one launch at a time, quietly, with the same records
+    from tests import pyec
+    D = pyec.mul(pyec.G, 987654321)
+    seq = [pts[0]]
+    for _ in range(31):
+        seq.append(pyec.add(seq[-1], D))
+    run_hits, done = e.run(pts[0], D, 32, batch=16)
+    two = sorted(run_hits)
+    ref2 = sorted([(c, i, wd) for c, i, wd in e.step_multi(seq[:16])] + [(c, i, wd + 16) for c, i, wd in e.step_multi(seq[16:])])
+    run_ok = done == 32 and two == ref2
     print(json.dumps({"N": N, "points_per_thread": info["points_per_thread"], "bytes_chain": info["bytes_chain"], "setup_s": round(t1 - t0, 2),
                       "launch_s": round(t2 - t1, 3), "giant_steps_per_s": 2 * N * 16 / (t2 - t1), "records": len(multi),
-                      "planted_found": ok_plant, "multi_equals_single": multi == single}))
-    assert ok_plant and multi == single
+                      "planted_found": ok_plant, "multi_equals_single": multi == single, "run_two_launches_equals_step_multi": run_ok, "run_records": len(two)}))
+    assert ok_plant and multi == single and run_ok
