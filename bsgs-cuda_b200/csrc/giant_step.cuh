@@ -504,6 +504,13 @@ __global__ void k_debug_field(int op, const uint32_t* a, const uint32_t* b, uint
         case 5: fp::fe_copy(z, x); fp::fe_canon(z); break;
         case 6: { uint64_t k = fp::fe_add_low64_canon(x, y); z[0] = (uint32_t)k; z[1] = (uint32_t)(k >> 32); break; }
         case 7: { uint64_t k = double_x_low64(x, y); z[0] = (uint32_t)k; z[1] = (uint32_t)(k >> 32); break; }
+        case 8: {                                          // reduce512 of the 512-bit value (y << 256) | x, incl. its out-of-line rare tail
+            uint32_t v[16];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { v[j] = x[j]; v[8 + j] = y[j]; }
+            fp::reduce512(z, v);
+            break;
+        }
     }
 #pragma unroll
     for (int j = 0; j < 8; j++) r[8 * i + j] = z[j];

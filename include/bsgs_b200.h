@@ -161,7 +161,8 @@ int  bsgs_set_option(bsgs_ctx *ctx, const char *name, int64_t value);
 /* -- diagnostics ---------------------------------------------------------------------------- */
 /* element-wise field operation on n pairs of 8 x u32 little-endian limbs, executed on the device
  * (op: 0 mul, 1 sqr, 2 inv, 3 sub(canonical), 4 add(lazy), 5 canonicalise, 6 low64 of canonical
- * (a+b), 7 low64 of X(2P) given (Px, 1/(2Py))).  Used by the parity tests of the limb arithmetic. */
+ * (a+b), 7 low64 of X(2P) given (Px, 1/(2Py)), 8 reduction of the 512-bit value (b << 256) | a).  Used by the
+ * parity tests of the limb arithmetic. */
 int  bsgs_debug_field(int device, int op, const uint32_t *a, const uint32_t *b, uint32_t *r, uint32_t n);
 /* the giant-step kernel's own key extraction (the square of lambda taken without reduction, the key read
  * off its low 64 bits and its limbs of weight >= 2^224, plus the out-of-line exact path it falls back to for

@@ -43,6 +43,33 @@ def test_field_ops_on_device(pkg):
     assert [g & M64 for g in got] == [pyec.add(p, p)[0] & M64 for p in pts]
 
 
+def test_reduction_rare_tail_on_device(pkg):
+    """reduce512 with its out-of-line tail (about 2^-22 of the calls) ON THE DEVICE: 512-bit inputs crafted so
+    that the first fold overflows by more than 32 bits (top2 = 1), so that the second fold carries out of limb
+    2 (limb 2 of the folded value all ones), and so that 2^256 wraps once more (limbs 3..7 all ones too)."""
+    rnd = random.Random(9)
+    C0 = 2**32 + 977
+    cases = [rnd.getrandbits(512) for _ in range(2000)] + [2**512 - 1, 0, 2**256 - 1, (2**256 - 1) << 256, P * P, (P - 1) * (2**256 - 1)]
+    for _ in range(300):
+        hi = rnd.getrandbits(256) | (1 << 255)
+        T = (hi * C0) >> 256
+        want_low = 2**256 - 1 - rnd.randrange(0, T * C0 + 1)
+        cases.append((hi << 256) | ((want_low - hi * C0) % 2**256))
+    for _ in range(100):                                             # top2 = 1
+        hi = 2**256 - 1 - rnd.getrandbits(20)
+        cases.append((hi << 256) | (2**256 - 1 - rnd.getrandbits(40)))
+    for j in range(300):                                             # carry out of limb 2 / full wrap
+        hi = rnd.getrandbits(256) >> 1
+        T = (hi * C0) >> 256
+        low = 2**64 - 1 - rnd.randrange(0, T * C0 + 1 if T else 1)
+        upper = (2**160 - 1) if j % 3 == 0 else rnd.getrandbits(160)
+        want_low = (upper << 96) | (0xFFFFFFFF << 64) | (low & (2**64 - 1))
+        cases.append((hi << 256) | ((want_low - hi * C0) % 2**256))
+    lo = [v & (2**256 - 1) for v in cases]; hi = [v >> 256 for v in cases]
+    got = pkg.native.debug_field(8, lo, hi)
+    assert all(g < 2**256 for g in got) and [g % P for g in got] == [v % P for v in cases]
+
+
 def test_low64_slow_path_on_device(pkg):
     """Values whose upper limbs are all ones exercise the exact branch of fe_add_low64_canon."""
     rnd = random.Random(11)
