@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256, 3) spin(uint32_t* out, uint32_t seed) {
 }
 
 // The arithmetic of one point-window exactly as the giant-step kernel does it (pass 1 + pass 2:
-// 5 multiplications, 2 squarings, 4 canonical subtractions, 1 lazy addition, 2 low-64 extractions),
+// 5 multiplications, 2 unreduced squarings, 3 canonical subtractions, 1 lazy addition, 2 key extractions from the wide square),
 // window constants in shared memory, giant coordinates and chain values in registers -- no global
 // memory, no probe, no ring.  Two giant steps per iteration.
 __global__ void __launch_bounds__(256, 3) spin_pw(uint32_t* out, uint32_t seed) {
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256, 3) spin_pw(uint32_t* out, uint32_t seed) 
     uint64_t sink = 0;
 #pragma unroll 1
     for (int it = 0; it < ITER / 4; it++) {
-        uint32_t px[8], py[8], npx[8], d[8], invd[8], t[8], u[8], sum[8], lam[8], l2[8];
+        uint32_t px[8], py[8], npx[8], d[8], invd[8], t[8], sum[8], lam[8], l2[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) { px[i] = s_win[i]; py[i] = s_win[8 + i]; npx[i] = s_win[16 + i]; }
         px[7] &= 0x7FFFFFFFu; py[7] &= 0x7FFFFFFFu; npx[7] &= 0x7FFFFFFFu;
@@ -59,13 +59,17 @@ __global__ void __launch_bounds__(256, 3) spin_pw(uint32_t* out, uint32_t seed) 
         fp::fe_mul(t, inv, d);
 #pragma unroll
         for (int i = 0; i < 8; i++) inv[i] = t[i];
-        fp::fe_sub_canon(u, npx, qx);
+        const uint64_t t_lo = ((((uint64_t)npx[1]) << 32) | npx[0]) - ((((uint64_t)qx[1]) << 32) | qx[0]);
+        const int64_t t7 = (int64_t)npx[7] - (int64_t)qx[7];
+        uint32_t v[16]; bool ex;
         fp::fe_add_lazy(sum, py, qy);
-        fp::fe_mul(lam, sum, invd); fp::fe_sqr(l2, lam);
-        sink ^= fp::fe_add_low64_canon(l2, u);
+        fp::fe_mul(lam, sum, invd); fp::fe_sqr_wide(v, lam);
+        sink ^= fp::fe_key_from_wide(v, t_lo, t7, FP_KEY_THR, ex);
         fp::fe_sub_canon(sum, py, qy);
-        fp::fe_mul(lam, sum, invd); fp::fe_sqr(l2, lam);
-        sink += fp::fe_add_low64_canon(l2, u);
+        fp::fe_mul(lam, sum, invd); fp::fe_sqr_wide(v, lam);
+        sink += fp::fe_key_from_wide(v, t_lo, t7, FP_KEY_THR, ex) + (ex ? 1 : 0);
+#pragma unroll
+        for (int i = 0; i < 8; i++) l2[i] = v[i] ^ v[8 + i];
 #pragma unroll
         for (int i = 0; i < 7; i++) { qx[i] ^= l2[i]; qy[i] += lam[i]; cprev[i] ^= invd[i]; }      // next "giant"
         cprev[7] = (cprev[7] ^ invd[7]) & 0x7FFFFFFFu;
@@ -107,7 +111,7 @@ int main() {
     double pw = run_pw(sms, out);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"fe_mul_per_s\": %.4g, \"fe_sqr_per_s\": %.4g, \"giant_step_ceiling_per_s\": %.4g, "
            "\"point_window_arithmetic_steps_per_s\": %.4g, "
-           "\"how\": \"2.5 fe_mul + 1 fe_sqr per giant step, 3 CTAs x 256 threads per SM, registers only; point_window_arithmetic = the whole field arithmetic of one point-window (5 mul, 2 sqr, 4 sub, 1 add, 2 low-64) without memory or probe\", \"err\": \"%s\"}\n",
+           "\"how\": \"2.5 fe_mul + 1 fe_sqr per giant step, 3 CTAs x 256 threads per SM, registers only; point_window_arithmetic = the whole field arithmetic of one point-window (5 mul, 2 unreduced sqr, 3 sub, 1 add, 2 keys from the wide square) without memory or probe, ONE launch (its uneven tail included)\", \"err\": \"%s\"}\n",
            pr.name, sms, mul, sqr, ceil_steps, pw, cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
