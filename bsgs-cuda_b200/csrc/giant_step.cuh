@@ -5,16 +5,22 @@
 // the baby-step table -- the work of W launches of the reference kernel `_test1`
 // (1_9_7File.pb:5181-23979; PASS 1 PTX197:L149-1297, inversion L1319-26062, PASS 2 L26955-36020).
 //
-// Structure (third iteration; the measurements that led here are in DESIGN.md and profiles/):
+// Structure (fourth iteration; the measurements that led here are in DESIGN.md 4.1 and profiles/):
 //   * limb products are single IMAD.WIDE.U32 issues with predicate carries (fp.cuh) instead of the
 //     reference's mad.lo + mad.hi pairs; the IMAD.WIDE pipe (measured 30.7 lanes/clk/SM) is the
 //     roofline of this kernel;
 //   * one Fermat inversion per thread covers PP*W points (reference: p points) and uses the
 //     255S+15M addition chain (reference: 255 + 249 generic multiplications);
-//   * one flat loop over (giant row r, window w): window constants live in shared memory and the
+//   * rows outside, windows inside, ONE loop body: window constants live in shared memory and the
 //     hot loop holds exactly 4 inlined multiplications + 2 squarings, so that it stays inside the
 //     instruction cache (the first kernel unrolled the windows: 118 KB of code, 35 % of stall
 //     samples were instruction-fetch);
+//   * the candidate's square is not reduced: X is used only through the low 64 bits of its canonical
+//     value, which follow from a few limbs of the 512-bit square (fp::fe_key_from_wide); 2^-29 of the
+//     candidates take an out-of-line exact path;
+//   * the warps of one launch do not finish together (the first warp of an SM is done after 58 % of the
+//     kernel): the library keeps two launches in flight on two streams (bsgs_b200.cu, "lanes"), so this
+//     kernel is written to share an SM with CTAs of its successor -- own chain and record buffers per lane;
 //   * giant coordinates are 128-bit vectors, SoA across threads: every warp load is one fully
 //     coalesced 512-byte transaction;
 //   * the CSR table of the reference (offset pair -> binary search: two dependent random reads) is
