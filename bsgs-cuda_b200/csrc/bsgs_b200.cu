@@ -115,7 +115,7 @@ extern "C" int bsgs_create(bsgs_ctx** out, int device, uint32_t T, uint32_t B, u
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_verdict, (size_t)ctx->hit_cap * 4);
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_verdict, (size_t)ctx->hit_cap * 4);
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_hits, 16 + (size_t)ctx->hit_cap * 12);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_hits, 0, 16, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_hits, 0, 16 + (size_t)ctx->hit_cap * 12, ctx->stream);      // whole buffer: the eager read-back copies record slots beyond the count
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { int rc = e == cudaErrorMemoryAllocation ? BSGS_E_NOMEM : BSGS_E_CUDA; bsgs_destroy(ctx); cudaGetLastError(); return rc; }
     compute_geometry(ctx);
@@ -555,7 +555,7 @@ static int ensure_lane2(bsgs_ctx* ctx) {
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_hits2, 16 + (size_t)ctx->hit_cap * 12);
     if (e == cudaSuccess && !ctx->e2) e = cudaEventCreate(&ctx->e2);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_hits2, 0, 16, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_hits2, 0, 16 + (size_t)ctx->hit_cap * 12, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         cudaGetLastError();
