@@ -37,7 +37,7 @@ CompilerEndIf
   bsgs_destroy(*ctx)                                                   ; cuMemFree / cuCtxDestroy, 2537-2548
   bsgs_strerror(status.l)
   bsgs_last_cuda_error(*ctx)
-  bsgs_set_option(*ctx, name.p-ascii, value.q)                         ; "verify", "blocks_per_sm", "block", "max_windows", "l2_fetch"
+  bsgs_set_option(*ctx, name.p-ascii, value.q)                         ; "verify", "overlap", "blocks_per_sm", "block", "max_windows", "l2_fetch"
   bsgs_upload_giants(*ctx, *g2, bytes.i)                               ; cuMemcpyHtoD of *GiantArrPacked, 2337
   bsgs_upload_ht(*ctx, *htgpu, bytes.i)                                ; cuMemcpyHtoD of *GpuHT, 2350
   bsgs_upload_htcpu(*ctx, *htcpu, bytes.i)                             ; same table with payloads: device-side verification
@@ -48,7 +48,7 @@ CompilerEndIf
   bsgs_ht_export(*ctx, kind.l, *out, bytes.i)                          ; kind 0: _htGPUv0.BIN image, 1: _htCPUv0.BIN image
   bsgs_step(*ctx, *px, *py, *hits, cap.l, *nhits)                      ; one launch, 2435-2509
   bsgs_step_multi(*ctx, nwin.l, *pxy, *hits, cap.l, *nhits)
-  bsgs_run(*ctx, *p0xy, *dxy, nwindows.q, batch.l, stop_after_hits.l, *hits, cap.l, *nhits, *windows_done)
+  bsgs_run(*ctx, *p0xy, *dxy, nwindows.q, batch.l, stop_after_hits.l, *hits, cap.l, *nhits, *windows_done)   ; GetJob loop; two launches in flight when nwindows > batch
   bsgs_device_count(*count)                                            ; start-up listing + Tune, 778-860, 324-431
   bsgs_device_query(device.l, *devinfo)
 EndImport

@@ -99,3 +99,11 @@ def test_purebasic_binding_lists_only_declared_functions():
             assert re.search(r"#define BSGS_MAX_WINDOWS\s+%s\b" % val, hdr)
         else:
             assert re.search(r"\b%s\s*=\s*%s\b" % (name, val), hdr), name
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 with no C++ or CUDA types in any signature."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "bsgs_b200.h"\nint main(void) { return bsgs_strerror(0) == 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
