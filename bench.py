@@ -564,7 +564,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nwin", type=int, default=16, help="GetJob windows per launch")
     ap.add_argument("--blocks-per-sm", type=int, default=3)
-    ap.add_argument("--block", type=int, default=256, help="threads per CTA: 256 (x blocks-per-sm) or 320 (x 2)")
+    ap.add_argument("--block", type=int, default=256, help="threads per CTA: 256 (x blocks-per-sm), 320 (x 2), 128 (x 6) or 64 (x 12)")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (32|64|128), 0 = leave")
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--synthetic-table", action="store_true", help="uniform random keys instead of the real baby-step table")

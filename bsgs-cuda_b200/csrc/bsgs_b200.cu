@@ -156,9 +156,13 @@ extern "C" int bsgs_set_option(bsgs_ctx* ctx, const char* name, int64_t value) {
     }
     if (ctx->d_gx || ctx->d_buckets) return BSGS_E_STATE;       // geometry is baked into the layouts
     if (!strcmp(name, "blocks_per_sm")) { if (value < 1 || value > 3) return BSGS_E_ARG; ctx->blocks_per_sm = (uint32_t)value; compute_geometry(ctx); return BSGS_OK; }
-    if (!strcmp(name, "block")) {                               // threads per CTA: 256 (x blocks_per_sm) or 320 (x 2)
-        if (value != 256 && value != 320) return BSGS_E_ARG;
-        ctx->block = (uint32_t)value; if (value == 320) ctx->blocks_per_sm = 2; compute_geometry(ctx); return BSGS_OK;
+    if (!strcmp(name, "block")) {                               // threads per CTA: 256 (x blocks_per_sm), 320 (x 2), 128 (x 6) or 64 (x 12)
+        if (value != 256 && value != 320 && value != 128 && value != 64) return BSGS_E_ARG;
+        ctx->block = (uint32_t)value;
+        if (value == 320) ctx->blocks_per_sm = 2;
+        if (value == 128) ctx->blocks_per_sm = 6;
+        if (value == 64) ctx->blocks_per_sm = 12;
+        compute_geometry(ctx); return BSGS_OK;
     }
     if (!strcmp(name, "max_windows")) { if (value < 1 || value > BSGS_MAX_WINDOWS) return BSGS_E_ARG; ctx->max_windows = (uint32_t)value; return BSGS_OK; }
     if (!strcmp(name, "l2_fetch")) {                            // device-wide: DRAM->L2 fetch granularity for the random sector reads
@@ -412,6 +416,8 @@ static cudaError_t launch_emit_k(const bsgs_ctx* c, const gs::Tables& tb, const 
 }
 static cudaError_t launch_emit(const bsgs_ctx* c, const gs::Tables& tb, const gs::WinParams& wp, int nwin) {
     if (c->block == 320) return launch_emit_k<320, 2>(c, tb, wp, nwin);
+    if (c->block == 128) return launch_emit_k<128, 6>(c, tb, wp, nwin);
+    if (c->block == 64) return launch_emit_k<64, 12>(c, tb, wp, nwin);
     return c->blocks_per_sm >= 3 ? launch_emit_k<256, 3>(c, tb, wp, nwin) : launch_emit_k<256, 2>(c, tb, wp, nwin);
 }
 static int generate_baby_keys(bsgs_ctx* ctx, uint64_t* d_keys) {
@@ -535,6 +541,8 @@ static cudaError_t launch_k(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy, int 
 static cudaError_t launch_any(bsgs_ctx* c, uint32_t nwin, const uint8_t* pxy, int lane = 0) {
     if (nwin < 1 || nwin > BSGS_MAX_WINDOWS) return cudaErrorInvalidValue;
     if (c->block == 320) return launch_k<320, 2>(c, nwin, pxy, lane);                  // 5 warps per scheduler, 96 registers
+    if (c->block == 128) return launch_k<128, 6>(c, nwin, pxy, lane);                  // same 24 warps per SM in smaller CTAs: slots free sooner
+    if (c->block == 64) return launch_k<64, 12>(c, nwin, pxy, lane);
     switch (c->blocks_per_sm) {
         case 1: case 2: return launch_k<256, 2>(c, nwin, pxy, lane);
         case 3: return launch_k<256, 3>(c, nwin, pxy, lane);
