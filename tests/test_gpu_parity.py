@@ -433,6 +433,38 @@ def test_run_equals_stepwise(pkg, orc):
         assert ms > 0 and sorted((c, i) for c, i in e.step(pts[0])) == sorted((c, i) for c, i, win in hits if win == 0)
 
 
+@pytest.mark.parametrize("opts", [dict(block=128), dict(block=64), dict(block=320), dict(blocks_per_sm=2), dict(blocks_per_sm=1)])
+def test_every_launch_geometry_emits_the_same_records(pkg, orc, opts):
+    """The kernel is instantiated for 256 x 3 (default), 256 x 2, 320 x 2, 128 x 6 and 64 x 12 threads per SM: same records."""
+    T, B, p, w, htsz = 64, 20, 50, 30000, 11
+    Ppt, plant, cpu, gpu, g2 = build_case(orc, T, B, p, w, htsz, seed=99)
+    want = norm_hits(orc.launch(g2, T, B, p, gpu, htsz, Ppt))
+    with pkg.Engine(T, B, p, w, htsz, **opts) as e:
+        e.upload_giants(g2); e.upload_ht(gpu)
+        assert norm_hits(e.step(Ppt)) == want and set(plant) <= set(want)
+        pts = [Ppt, pyec.add(Ppt, pyec.G), pyec.add(Ppt, pyec.mul(pyec.G, 5))]
+        multi = sorted((wi, c, i) for c, i, wi in e.step_multi(pts))
+        assert multi == sorted((wi, c, 0 if c == 5 else i) for wi, pt in enumerate(pts) for c, i in orc.launch(g2, T, B, p, gpu, htsz, pt))
+
+
+def test_trace_diagnostics(pkg, orc):
+    """bsgs_debug_trace: per-warp {SM id, start, end of pass 1, end} of the last launch, in order."""
+    T, B, p, w, htsz = 64, 20, 50, 30000, 11
+    Ppt, plant, cpu, gpu, g2 = build_case(orc, T, B, p, w, htsz, seed=98)
+    with pkg.Engine(T, B, p, w, htsz) as e:
+        e.upload_giants(g2); e.upload_ht(gpu)
+        with pytest.raises(pkg.BsgsError):
+            e.trace()                                              # not enabled
+        e._ck(e.L.bsgs_set_option(e.h, b"trace", 1), "trace")
+        hits = norm_hits(e.step(Ppt))
+        tr = e.trace()
+        info = e.info()
+        assert tr.shape == (info["grid"] * info["block"] // 32, 4)
+        assert (tr[:, 0] < info["sm_count"]).all() and (tr[:, 1] <= tr[:, 2]).all() and (tr[:, 2] <= tr[:, 3]).all() and (tr[:, 1] > 0).all()
+        e._ck(e.L.bsgs_set_option(e.h, b"trace", 0), "trace")
+        assert norm_hits(e.step(Ppt)) == hits
+
+
 def test_error_behaviour(pkg):
     with pytest.raises(pkg.BsgsError):
         pkg.Engine(1 << 12, 1 << 12, 1 << 8, 1000, 10)              # N >= 2^31
